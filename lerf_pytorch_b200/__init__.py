@@ -1,0 +1,19 @@
+"""lerf_pytorch_b200 -- B200-native (sm_100a) LUT inference hot path of LeRF.
+
+Drop-in for the reference's (ddlee-cn/LeRF-PyTorch) LUT evaluation path only:
+``FourSimplexInterpFaster`` (resample/eval_lut_sr.py:24-470), the ``*Resize2d*`` / ``*Warp2d*`` operators
+(resize_right/resize_right2d_numpy.py) and the per-image bodies of eval_lut_sr.py / eval_lut_warp.py.
+Everything runs in hand-written CUDA behind the C ABI in include/lerf_b200.h; there is no CPU fallback.
+"""
+from ._lib import LerfError, lib  # noqa: F401
+from .lut_interp import FourSimplexInterpFaster, lut_stage1, lut_stage2, lut_stages, mode_pad_dict  # noqa: F401
+from .luts import LutSet, load_lut_dict  # noqa: F401
+from .pipeline import LerfSR, LerfWarp  # noqa: F401
+from .resize_right2d import (  # noqa: F401
+    AmplifiedLinearResize2d, AmplifiedLinearResize2dNumpy, AmplifiedLinearResize2dTorch,
+    AmplifiedLinearWarp2d, AmplifiedLinearWarp2dNumpy, AmplifiedLinearWarp2dTorch,
+    NearestWarp2d, NearestWarp2dNumpy, NearestWarp2dTorch,
+    SteeringGaussianResize2d, SteeringGaussianResize2dNumpy, SteeringGaussianResize2dTorch,
+    SteeringGaussianWarp2d, SteeringGaussianWarp2dNumpy, SteeringGaussianWarp2dTorch, sr_axis_tables)
+
+__version__ = "0.1.0"

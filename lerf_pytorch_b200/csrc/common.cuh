@@ -1,0 +1,69 @@
+// Shared device/host helpers for liblerf_b200.so (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "lerf_b200.h"
+
+namespace lerf {
+
+extern thread_local std::string g_last_error;
+extern thread_local long long g_launches;
+
+int fail(int code, const char* fmt, ...);
+
+#define LERF_CUDA(expr)                                                                      \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess)                                                                  \
+      return ::lerf::fail(LERF_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                          __FILE__, __LINE__);                                               \
+  } while (0)
+
+// Call after every kernel launch: counts it and surfaces launch-configuration errors.
+#define LERF_LAUNCHED()                                                                      \
+  do {                                                                                       \
+    ++::lerf::g_launches;                                                                    \
+    cudaError_t e__ = cudaGetLastError();                                                    \
+    if (e__ != cudaSuccess)                                                                  \
+      return ::lerf::fail(LERF_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), \
+                          __FILE__, __LINE__);                                               \
+  } while (0)
+
+constexpr int kL = 17;                 // LUT grid points per axis (interval 4)
+constexpr int kEntries = kL * kL * kL * kL;  // 83521
+constexpr int kStrideA = kL * kL * kL;       // 4913
+constexpr int kStrideB = kL * kL;            // 289
+constexpr int kStrideC = kL;                 // 17
+constexpr int kStrideAll = kStrideA + kStrideB + kStrideC + 1;  // 5220: base -> p1111
+
+struct InAddr {  // strided uint8 source (see lerf_lut_stage1 in lerf_b200.h)
+  int channels;
+  long long batch_stride, chan_stride, row_stride, pix_stride;
+};
+
+struct lerf_luts_impl {
+  int device;
+  int oC2;
+  void* block;          // one allocation holding every table (L2 window target)
+  size_t block_bytes;
+  const int8_t* s1[3];  // s, c, t            int8 [83521]
+  const void* s2[6];    // s r0, s r1, c r0, c r1, t r0, t r1
+                        // oC2 == 3: uint32 per entry = bytes (c0, c1, c2, 0);  oC2 == 1: int8
+};
+
+struct lerf_sr_plan_impl {
+  int device;
+  int H, W, oH, oW;
+  int* left_y;     // device [oH]   first tap row (unpadded, may be -1)
+  int* left_x;     // device [oW]
+  double* dist_y;  // device [2*oH] distance to tap 0 / tap 1 (row axis)
+  double* dist_x;  // device [2*oW]
+  int* h_left_y;   // host copy (row-band planning)
+  int int_scale;   // S if out = S*in on both axes with the periodic phase pattern, else 0
+};
+
+}  // namespace lerf

@@ -1,0 +1,182 @@
+"""Whole-path engines: the body of ``eltr._worker`` of the reference's eval scripts without file I/O.
+
+* ``LerfSR``   <- resample/eval_lut_sr.py:541-665   (LUT stages -> set_shape -> resize -> uint8 epilogue)
+* ``LerfWarp`` <- resample/eval_lut_warp.py:100-222 (LUT stages -> set_shape -> mask -> warp -> uint8 epilogue)
+
+Both take uint8 images as PIL decodes them ([H,W,C] or a batch [B,H,W,C]) that are already CUDA tensors,
+and return CUDA tensors; ``LerfSR.run_host`` is the host-to-host entry (pinned uint8 in, pinned uint8 out)
+used for end-to-end timing.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import LERF_KIND_GAUSS, LERF_KIND_LINEAR
+from .lut_interp import lut_stage1, lut_stage2
+from .luts import LutSet
+from .resize_right2d import (AmplifiedLinearResize2d, AmplifiedLinearWarp2d, SteeringGaussianResize2d,
+                             SteeringGaussianWarp2d, _FMT)
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class LerfSR(object):
+    """Arbitrary-scale SR through the LUT path for images of one size."""
+
+    def __init__(self, luts, scale_h, scale_w=None, max_sigma=10, support_sz=2):
+        assert isinstance(luts, LutSet)
+        self.luts = luts
+        self.scale = (float(scale_h), float(scale_h if scale_w is None else scale_w))
+        if luts.linear:
+            self.resizer = AmplifiedLinearResize2d()  # eval_lut_sr.py:483: constructed without arguments
+        else:
+            self.resizer = SteeringGaussianResize2d(support_sz=support_sz, max_sigma=max_sigma)
+        self.kind = LERF_KIND_LINEAR if luts.linear else LERF_KIND_GAUSS
+        self._shape = None
+        self._scratch = {}
+        self._slots = None
+
+    def set_shape(self, H, W, C=3):
+        if self._shape != (H, W, C):
+            self.resizer.set_shape([C, H, W], scale_factors=list(self.scale))
+            self._shape = (H, W, C)
+        return self.resizer.out_sz
+
+    @property
+    def out_sz(self):
+        return self.resizer.out_sz
+
+    def _get_scratch(self, planes, H, W, device, slot=0):
+        need = _lib.lib().lerf_sr_scratch_bytes(planes, self.luts.oC, H, W)
+        cur = self._scratch.get(slot)
+        if cur is None or cur.numel() < need or cur.device != device:
+            cur = self._scratch[slot] = torch.empty(need, dtype=torch.uint8, device=device)
+        return cur
+
+    def alloc_out(self, B, C, out_format, device):
+        oH, oW = self.out_sz
+        if out_format == "f32":
+            return torch.empty((B, C, oH, oW), dtype=torch.float32, device=device)
+        if out_format == "u8":
+            return torch.empty((B, C, oH, oW), dtype=torch.uint8, device=device)
+        return torch.empty((B, oH, oW, C), dtype=torch.uint8, device=device)
+
+    def __call__(self, img, out_format="f32", rows=None, out=None, layout="HWC", record=None, slot=0):
+        """img: uint8 CUDA [H,W,C] / [B,H,W,C] (layout 'HWC') or [C,H,W] / [B,C,H,W] ('CHW').
+
+        Returns float32 [B,C,oH,oW] ('f32'), uint8 [B,C,oH,oW] ('u8') or uint8 [B,oH,oW,C] ('u8_hwc');
+        the batch dimension is dropped when the input had none.  ``rows=(oy0, oy1)`` restricts the work to an
+        output row band (the rest of ``out`` is left untouched) -- row-band sharding across GPUs.
+        ``record(name)``, if given, is called after each kernel launch (bench.py puts CUDA events there); the
+        launches are the same three lerf_sr_fused issues.
+        """
+        if img.dtype != torch.uint8 or not img.is_cuda:
+            raise ValueError("LerfSR needs a uint8 CUDA tensor")
+        squeeze = img.dim() == 3
+        if squeeze:
+            img = img.unsqueeze(0)
+        img = img.contiguous()
+        if layout == "HWC":
+            B, H, W, C = img.shape
+            addr = (C, H * W * C, 1, W * C, C)
+        else:
+            B, C, H, W = img.shape
+            addr = (C, C * H * W, H * W, W, 1)
+        self.set_shape(H, W, C)
+        dev = img.device
+        oH, oW = self.out_sz
+        if out is None:
+            out = self.alloc_out(B, C, out_format, dev)
+        oy0, oy1 = (0, oH) if rows is None else rows
+        scratch = self._get_scratch(B * C, H, W, dev, slot)
+        with torch.cuda.device(dev):
+            self.luts.pin_l2()
+            if record is not None and rows is None:
+                L, st, P = _lib.lib(), _stream_ptr(dev), B * C
+                feat = scratch[:P * H * W]
+                codes = scratch[(P * H * W + 255) // 256 * 256:]
+                _lib.check(L.lerf_lut_stage1(self.luts.handle, img.data_ptr(), P, H, W, addr[0], addr[1], addr[2], addr[3],
+                                             addr[4], 0, H, feat.data_ptr(), st))
+                record("lut_stage1")
+                _lib.check(L.lerf_lut_stage2(self.luts.handle, feat.data_ptr(), P, H, W, 0, H, codes.data_ptr(), st))
+                record("lut_stage2")
+                _lib.check(L.lerf_resize_sr(self.kind, self.resizer._get_plan(dev), feat.data_ptr(), codes.data_ptr(), P, C,
+                                            float(self.resizer.max_sigma), 0, oH, out.data_ptr(), _FMT[out_format], st))
+                record("resize_sr")
+                return out[0] if squeeze else out
+            _lib.check(_lib.lib().lerf_sr_fused(self.luts.handle, self.kind, self.resizer._get_plan(dev), img.data_ptr(),
+                                                B * C, addr[0], addr[1], addr[2], addr[3], addr[4],
+                                                float(self.resizer.max_sigma), oy0, oy1, scratch.data_ptr(),
+                                                out.data_ptr(), _FMT[out_format], _stream_ptr(dev)))
+        return out[0] if squeeze else out
+
+    def run_host(self, host_in, host_out, depth=3):
+        """Host-to-host entry: ``host_in`` pinned uint8 [B,H,W,C], ``host_out`` pinned uint8 [B,oH,oW,C].
+
+        Frames are pipelined over ``depth`` streams (H2D copy, the three kernels, D2H copy per frame) so PCIe
+        transfers overlap compute.  Returns after everything has landed in ``host_out``.
+        """
+        B, H, W, C = host_in.shape
+        self.set_shape(H, W, C)
+        oH, oW = self.out_sz
+        dev = self.luts.device
+        if self._slots is None or self._slots[0] != (H, W, C, depth):
+            slots = []
+            for _ in range(depth):
+                slots.append((torch.cuda.Stream(dev), torch.empty((H, W, C), dtype=torch.uint8, device=dev),
+                              torch.empty((oH, oW, C), dtype=torch.uint8, device=dev)))
+            self._slots = ((H, W, C, depth), slots)
+        slots = self._slots[1]
+        cur = torch.cuda.current_stream(dev)
+        for st, _, _ in slots:
+            st.wait_stream(cur)
+        for i in range(B):
+            st, d_in, d_out = slots[i % depth]
+            with torch.cuda.stream(st):
+                d_in.copy_(host_in[i], non_blocking=True)
+                self(d_in, out_format="u8_hwc", out=d_out.unsqueeze(0), slot=1 + i % depth)
+                host_out[i].copy_(d_out, non_blocking=True)
+        for st, _, _ in slots:
+            cur.wait_stream(st)
+        cur.synchronize()
+        return host_out
+
+    def stages(self, img, layout="HWC"):
+        """The intermediate products (feat uint8 [P,H,W], codes uint8 [P*oC,H,W]) for parity checks."""
+        feat = lut_stage1(self.luts, img, layout)
+        return feat, lut_stage2(self.luts, feat)
+
+
+class LerfWarp(object):
+    """Homographic warping through the LUT path (one image per call, like the reference)."""
+
+    def __init__(self, luts, max_sigma=10, support_sz=2, border=4):
+        assert isinstance(luts, LutSet)
+        self.luts = luts
+        self.border = border  # eval_lut_warp.py:36
+        if luts.linear:
+            self.warper = AmplifiedLinearWarp2d()  # eval_lut_warp.py:38
+        else:
+            self.warper = SteeringGaussianWarp2d(support_sz=support_sz, max_sigma=max_sigma)
+
+    def __call__(self, img, matrix, out_hw, out_format="f32", with_mask=True):
+        """img uint8 CUDA [H,W,C]; matrix 3x3 input->output; out_hw = (oH, oW) of the target canvas.
+
+        Returns (out, mask): out float32/uint8 [C,oH,oW] (or [oH,oW,C] for 'u8_hwc'), mask uint8 [oH,oW].
+        """
+        if img.dtype != torch.uint8 or not img.is_cuda or img.dim() != 3:
+            raise ValueError("LerfWarp needs a uint8 CUDA tensor [H,W,C]")
+        H, W, C = img.shape
+        self.luts.pin_l2()
+        feat = lut_stage1(self.luts, img, "HWC")
+        codes = lut_stage2(self.luts, feat)
+        self.warper.set_shape([C, H, W], matrix, [C, int(out_hw[0]), int(out_hw[1])])
+        res = self.warper.warp_codes(feat, codes, channels=C, out_format=out_format, with_mask=with_mask,
+                                     mask_border=self.border)
+        out, mask = res if with_mask else (res, None)
+        if out_format == "u8_hwc":
+            out = out[0]
+        return out, mask

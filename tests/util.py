@@ -53,3 +53,20 @@ def random_luts(seed, oC2=3, modes="sct"):
         for r in "01":
             luts["s2_%sr%s" % (m, r)] = rng.integers(-128, 128, size=(17 ** 4, oC2)).astype(np.int8)
     return luts
+
+
+def psnr_y(gt_hwc_u8, out_hwc_u8, shave):
+    """PSNR on the Y channel as the reference's eval computes it (common/utils.py:46-76 _rgb2ycbcr,
+    :138-151 PSNR with shave_border = scale; eval_lut_sr.py:735-742 crops both to the common size)."""
+    gt, out = np.asarray(gt_hwc_u8), np.asarray(out_hwc_u8)
+    h, w = min(gt.shape[0], out.shape[0]), min(gt.shape[1], out.shape[1])
+    gt, out = gt[:h, :w], out[:h, :w]
+    T0 = np.array([0.256788235294118, 0.504129411764706, 0.097905882352941])
+
+    def y(img):
+        return np.dot(img.reshape(-1, 3), T0).reshape(img.shape[:2]) + 16
+
+    d = (y(out).astype(np.float32) - y(gt).astype(np.float32))
+    if shave > 0:
+        d = d[shave:-shave, shave:-shave]
+    return float(20 * np.log10(255.0 / np.sqrt(np.mean(np.power(d, 2)))))
