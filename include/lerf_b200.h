@@ -97,6 +97,10 @@ int lerf_lut_stage1(const lerf_luts_t* luts, const uint8_t* in, int planes, int 
 int lerf_lut_stage2(const lerf_luts_t* luts, const uint8_t* feat, int planes, int H, int W, int y0,
                     int y1, uint8_t* codes, lerf_stream_t stream);
 
+/* Testing / tuning hook for lerf_lut_stage1: 0 = choose by size, 1 = always the L1-path kernel, 2 = always the
+ * persistent shared-memory-table kernel.  All variants produce identical bytes. */
+void lerf_debug_stage1_variant(int v);
+
 /* ---- SR geometry plan --------------------------------------------------------------------------
  * Replaces Resize2dNumpy.set_shape / get_distance (resize_right2d_numpy.py:18-140) for support 2.
  * The per-axis tables are computed by the caller in float64 in the reference's operation order
@@ -120,6 +124,9 @@ void lerf_sr_plan_destroy(lerf_sr_plan_t* plan);
 int lerf_resize_sr(int kind, const lerf_sr_plan_t* plan, const uint8_t* feat, const uint8_t* codes,
                    int planes, int channels, float max_sigma, int oy0, int oy1, void* out,
                    int out_format, lerf_stream_t stream);
+
+/* Testing hook: when on, integer scales also take the generic-scale kernel (the two must agree). */
+void lerf_debug_force_generic(int on);
 
 /* Same operator on float32 image / float32 hyper planes in [0,1], for callers that bring their own
  * (non-LUT) hyper-parameters exactly like the reference's resize(input, rho, sigma_x, sigma_y).

@@ -48,6 +48,7 @@ struct InAddr {  // strided uint8 source (see lerf_lut_stage1 in lerf_b200.h)
 struct lerf_luts_impl {
   int device;
   int oC2;
+  int num_sms;
   void* block;          // one allocation holding every table (L2 window target)
   size_t block_bytes;
   const int8_t* s1[3];  // s, c, t            int8 [83521]
@@ -64,6 +65,12 @@ struct lerf_sr_plan_impl {
   double* dist_x;  // device [2*oW]
   int* h_left_y;   // host copy (row-band planning)
   int int_scale;   // S if out = S*in on both axes with the periodic phase pattern, else 0
+  int ph_y, ph_x;  // periodic geometry: the outputs whose first tap is l are S*l + ph + m, m = 0..S-1
+  double ph_dist_y[8][2], ph_dist_x[8][2];  // their distances to tap 0 / tap 1
 };
+
+// resample_int.cu
+int resize_sr_int_gauss(const lerf_sr_plan_impl* P, const uint8_t* feat, const uint8_t* codes, int planes, int channels,
+                        float max_sigma, int oy0, int oy1, void* out, int fmt, cudaStream_t st);
 
 }  // namespace lerf

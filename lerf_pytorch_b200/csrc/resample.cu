@@ -291,6 +291,30 @@ static int launch_warp(const ImgT* img, Hyp hyp, const WarpGeom& g, int planes, 
   return LERF_OK;
 }
 
+// Periodic-geometry detection for integer scales: returns S (2,3,4,8) if out = S*in and the host tables repeat
+// with period S (left exactly, distances to 1e-9), else 0.
+static int detect_int_scale(int in, int out, const int* left, const double* dist, int& ph, double tab[8][2]) {
+  if (in < 2 || out % in) return 0;
+  const int S = out / in;
+  if (S != 2 && S != 3 && S != 4 && S != 8) return 0;
+  int o0 = -1;
+  for (int o = 0; o < out && o0 < 0; ++o)
+    if (left[o] == 0) o0 = o;
+  if (o0 < 0 || o0 >= S || o0 + S > out) return 0;
+  ph = o0;
+  for (int m = 0; m < S; ++m)
+    for (int k = 0; k < 2; ++k) tab[m][k] = dist[2 * (ph + m) + k];
+  for (int o = 0; o < out; ++o) {
+    const int d = o - ph;
+    const int l = d >= 0 ? d / S : -((-d + S - 1) / S);
+    const int m = d - l * S;
+    if (left[o] != l) return 0;
+    for (int k = 0; k < 2; ++k)
+      if (fabs(dist[2 * o + k] - tab[m][k]) > 1e-9) return 0;
+  }
+  return S;
+}
+
 static int fill_geom(WarpGeom& g, int H, int W, int oH, int oW, const double minv[9], int pad0_y, int pad0_x,
                      int mpy, int mpx, int border) {
   if (!minv) return fail(LERF_EINVAL, "warp: minv is null");
@@ -305,6 +329,8 @@ static int fill_geom(WarpGeom& g, int H, int W, int oH, int oW, const double min
 }  // namespace lerf
 
 using namespace lerf;
+
+static bool g_force_generic = false;
 
 extern "C" {
 
@@ -338,6 +364,9 @@ int lerf_sr_plan_create(int H, int W, int oH, int oW, const int32_t* left_y, con
   }
   P->h_left_y = (int*)malloc(sizeof(int) * oH);
   memcpy(P->h_left_y, left_y, sizeof(int) * oH);
+  const int sy = detect_int_scale(H, oH, left_y, dist_y, P->ph_y, P->ph_dist_y);
+  const int sx = detect_int_scale(W, oW, left_x, dist_x, P->ph_x, P->ph_dist_x);
+  P->int_scale = (sy && sy == sx) ? sy : 0;
   *out = reinterpret_cast<lerf_sr_plan_t*>(P);
   return LERF_OK;
 }
@@ -368,10 +397,18 @@ int lerf_resize_sr(int kind, const lerf_sr_plan_t* plan, const uint8_t* feat, co
   if (rc) return rc;
   if (planes == 0 || oy0 == oy1) return LERF_OK;
   CodeSrc hyp{codes};
-  if (kind == LERF_KIND_GAUSS)
+  if (kind == LERF_KIND_GAUSS) {
+    if (P->int_scale && !g_force_generic) {  // periodic geometry: cell-owner kernel (resample_int.cu)
+      rc = resize_sr_int_gauss(P, feat, codes, planes, channels, max_sigma, oy0, oy1, out, out_format, (cudaStream_t)stream);
+      if (rc != -1) return rc;
+    }
     return launch_sr<LERF_KIND_GAUSS>(P, feat, hyp, planes, channels, max_sigma, oy0, oy1, out, out_format, (cudaStream_t)stream);
+  }
   return launch_sr<LERF_KIND_LINEAR>(P, feat, hyp, planes, channels, max_sigma, oy0, oy1, out, out_format, (cudaStream_t)stream);
 }
+
+/* Testing hook: route integer scales through the generic kernel too (parity tests compare both). */
+void lerf_debug_force_generic(int on) { g_force_generic = on != 0; }
 
 int lerf_resize_sr_f32(int kind, const lerf_sr_plan_t* plan, const float* img, const float* h0, const float* h1,
                        const float* h2, int planes, float max_sigma, float* out, lerf_stream_t stream) {

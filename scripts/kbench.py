@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""GPU box: per-kernel device time (us per 2040x1356 frame) of the hot path and its tuning variants."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+import lerf_pytorch_b200 as lp  # noqa: E402
+
+B = int(os.environ.get("KB_FRAMES", "4"))
+REP = int(os.environ.get("KB_REP", "10"))
+dev = torch.device("cuda", 0)
+luts = lp.LutSet(lp.load_lut_dict(bench.LUT_DIR), device=dev)
+luts.pin_l2()
+L = lp.lib()
+
+
+def timeit(fn):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(REP):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / REP / B * 1e3  # us per frame
+
+
+for kind in ("natural", "uniform"):
+    frames = (bench.natural_frames_gpu if kind == "natural" else bench.uniform_frames_gpu)(B, 3000, dev)
+    ref_feat = None
+    for v, name in ((0, "L1-path minb3"), (2, "smem 32x32/1024thr"), (3, "smem 32x16/512thr"), (4, "L1 minb4"),
+                    (11, "EXP same-address loads"), (12, "EXP no loads")):
+        L.lerf_debug_stage1_variant(v)
+        feat = lp.lut_stage1(luts, frames)
+        if ref_feat is None:
+            ref_feat = feat.clone()
+        assert v >= 11 or torch.equal(feat, ref_feat), "stage-1 variants disagree"
+        print("%-8s stage1 %-20s %8.1f us/frame" % (kind, name, timeit(lambda: lp.lut_stage1(luts, frames, out=feat))), flush=True)
+    L.lerf_debug_stage1_variant(0)
+    codes = lp.lut_stage2(luts, ref_feat)
+    for v in (0, 1, 3, 5):
+        L.lerf_debug_stage1_variant(100 * v)
+        c2 = lp.lut_stage2(luts, ref_feat)
+        assert torch.equal(c2, codes)
+        print("%-8s stage2 %-20s %8.1f us/frame" % (kind, "minb%d" % v, timeit(lambda: lp.lut_stage2(luts, ref_feat, out=c2))), flush=True)
+    L.lerf_debug_stage1_variant(0)
+    rs = lp.SteeringGaussianResize2d(support_sz=2, max_sigma=10)
+    rs.set_shape([3, bench.H, bench.W], scale_factors=[4, 4])
+    for fmt in ("f32", "u8", "u8_hwc"):
+        out = rs.resize_codes(ref_feat, codes, out_format=fmt)
+        print("%-8s resize %-20s %8.1f us/frame" % (kind, "int-scale " + fmt, timeit(lambda: rs.resize_codes(ref_feat, codes, out_format=fmt, out=out))), flush=True)
+    L.lerf_debug_force_generic(1)
+    out = rs.resize_codes(ref_feat, codes)
+    print("%-8s resize %-20s %8.1f us/frame" % (kind, "generic f32", timeit(lambda: rs.resize_codes(ref_feat, codes, out=out))), flush=True)
+    L.lerf_debug_force_generic(0)

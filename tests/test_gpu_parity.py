@@ -330,3 +330,42 @@ def test_full_size_properties_cfg3(lp, luts):
     o = srs(const, out_format="f32")
     inner = o[:, 8:-8, 8:-8]
     assert float((inner - inner[:, :1, :1]).abs().max()) <= 1e-4
+
+
+@pytest.mark.parametrize("S", [2, 3, 4, 8])
+def test_int_scale_kernel_vs_generic_kernel_and_oracle(lp, orc, luts, S):
+    """The periodic-geometry (cell-owner) kernel and the generic kernel are two implementations of the same operator."""
+    ld, ls = luts["g"]
+    img = uniform_image(900 + S, 53, 71)
+    sr = lp.LerfSR(ls, S)
+    dimg = _cuda(img)
+    ref, _, _ = orc.lerf_sr(img, ld, S, S)
+    try:
+        outs = {}
+        for force in (0, 1):
+            lp.lib().lerf_debug_force_generic(force)
+            outs[force] = {f: sr(dimg, out_format=f).cpu().numpy() for f in ("f32", "u8", "u8_hwc")}
+    finally:
+        lp.lib().lerf_debug_force_generic(0)
+    for force in (0, 1):
+        err = _maxabs(outs[force]["f32"], ref)
+        print("S=%d %s kernel: max-abs err %.3g" % (S, "generic" if force else "int-scale", err))
+        assert err <= FP32_TOL
+        want = orc.to_uint8_hwc(ref)
+        assert np.max(np.abs(outs[force]["u8_hwc"].astype(int) - want.astype(int))) <= 1
+        assert np.array_equal(np.transpose(outs[force]["u8"], (1, 2, 0)), outs[force]["u8_hwc"])
+    assert float(np.max(np.abs(outs[0]["f32"].astype(np.float64) - outs[1]["f32"]))) <= 1e-4
+
+
+def test_extreme_hypers_no_nan(lp):
+    """All-taps-underflow hazard: sigma = max everywhere, rho = +-1, far taps -> weights ~ 2^-288."""
+    H, W = 12, 14
+    feat = torch.randint(0, 256, (3, H, W), dtype=torch.uint8, device="cuda")
+    for rho_code in (0, 255, 128):
+        codes = torch.full((9, H, W), 255, dtype=torch.uint8, device="cuda")
+        codes[0::3] = rho_code
+        for s in (2, 4, 3.5):
+            rs = lp.SteeringGaussianResize2d(support_sz=2, max_sigma=10)
+            rs.set_shape([3, H, W], scale_factors=[s, s])
+            out = rs.resize_codes(feat, codes)
+            assert bool(torch.isfinite(out).all())
