@@ -12,6 +12,7 @@ import lerf_pytorch_b200 as lp  # noqa: E402
 
 B = int(os.environ.get("KB_FRAMES", "4"))
 REP = int(os.environ.get("KB_REP", "10"))
+ONLY = os.environ.get("KB_ONLY", "")
 dev = torch.device("cuda", 0)
 luts = lp.LutSet(lp.load_lut_dict(bench.LUT_DIR), device=dev)
 luts.pin_l2()
@@ -19,6 +20,9 @@ L = lp.lib()
 
 
 def timeit(fn):
+    if os.environ.get("KB_NOTIME"):
+        fn()
+        return 0.0
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -31,11 +35,12 @@ def timeit(fn):
     return a.elapsed_time(b) / REP / B * 1e3  # us per frame
 
 
-for kind in ("natural", "uniform"):
+for kind in os.environ.get("KB_KINDS", "natural,uniform").split(","):
     frames = (bench.natural_frames_gpu if kind == "natural" else bench.uniform_frames_gpu)(B, 3000, dev)
     ref_feat = None
-    for v, name in ((0, "L1-path minb3"), (2, "smem 32x32/1024thr"), (3, "smem 32x16/512thr"), (4, "L1 minb4"),
-                    (11, "EXP same-address loads"), (12, "EXP no loads")):
+    s1_variants = ((0, "L1-path minb3"), (2, "smem 32x32/1024thr"), (3, "smem 32x16/512thr"), (4, "L1 minb4"),
+                   (11, "EXP same-address loads"), (12, "EXP no loads"))
+    for v, name in (s1_variants[:1] if ONLY == "prod" else s1_variants):
         L.lerf_debug_stage1_variant(v)
         feat = lp.lut_stage1(luts, frames)
         if ref_feat is None:
@@ -44,7 +49,7 @@ for kind in ("natural", "uniform"):
         print("%-8s stage1 %-20s %8.1f us/frame" % (kind, name, timeit(lambda: lp.lut_stage1(luts, frames, out=feat))), flush=True)
     L.lerf_debug_stage1_variant(0)
     codes = lp.lut_stage2(luts, ref_feat)
-    for v in (0, 1, 3, 5):
+    for v in ((0,) if ONLY == "prod" else (0, 1, 3, 5)):
         L.lerf_debug_stage1_variant(100 * v)
         c2 = lp.lut_stage2(luts, ref_feat)
         assert torch.equal(c2, codes)
