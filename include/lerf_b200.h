@@ -97,9 +97,10 @@ int lerf_lut_stage1(const lerf_luts_t* luts, const uint8_t* in, int planes, int 
 int lerf_lut_stage2(const lerf_luts_t* luts, const uint8_t* feat, int planes, int H, int W, int y0,
                     int y1, uint8_t* codes, lerf_stream_t stream);
 
-/* Testing / tuning hook for lerf_lut_stage1: 0 = choose by size, 1 = always the L1-path kernel, 2 = always the
- * persistent shared-memory-table kernel.  All variants produce identical bytes. */
-void lerf_debug_stage1_variant(int v);
+/* Testing / tuning hook: selects the kernel behind lerf_lut_stage1 (stage = 1) / lerf_lut_stage2 (stage = 2).
+ * 0 = production choice; 1..19 = the row-major-table kernel (first implementation, kept for A/B); 20+ = tuning
+ * variants of the cell-packed-table kernel.  All non-experimental variants produce identical bytes. */
+void lerf_debug_lut_variant(int stage, int variant);
 
 /* ---- SR geometry plan --------------------------------------------------------------------------
  * Replaces Resize2dNumpy.set_shape / get_distance (resize_right2d_numpy.py:18-140) for support 2.

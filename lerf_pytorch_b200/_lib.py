@@ -29,7 +29,7 @@ PROTOTYPES = {
     "lerf_sr_plan_destroy": (None, [_c_p]),
     "lerf_resize_sr": (_c_i, [_c_i, _c_p, _c_p, _c_p, _c_i, _c_i, _c_f, _c_i, _c_i, _c_p, _c_i, _c_p]),
     "lerf_debug_force_generic": (None, [_c_i]),
-    "lerf_debug_stage1_variant": (None, [_c_i]),
+    "lerf_debug_lut_variant": (None, [_c_i, _c_i]),
     "lerf_resize_sr_f32": (_c_i, [_c_i, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_f, _c_p, _c_p]),
     "lerf_warp": (_c_i, [_c_i, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p, _c_i, _c_i, _c_f, _c_p, _c_i,
                          _c_p, _c_i, _c_i, _c_i, _c_p]),

@@ -54,6 +54,12 @@ struct lerf_luts_impl {
   const int8_t* s1[3];  // s, c, t            int8 [83521]
   const void* s2[6];    // s r0, s r1, c r0, c r1, t r0, t r1
                         // oC2 == 3: uint32 per entry = bytes (c0, c1, c2, 0);  oC2 == 1: int8
+  // cell-packed copies (lut_cell.cuh): 65536 cells; stage 1: 16 B per cell; stage 2: 16 B (oC 1) or 64 B (oC 3,
+  // channel k at [16k, 16k+16))
+  void* cell_block;
+  size_t cell_block_bytes;
+  const uint8_t* c1[3];
+  const uint8_t* c2[6];
 };
 
 struct lerf_sr_plan_impl {
@@ -68,6 +74,11 @@ struct lerf_sr_plan_impl {
   int ph_y, ph_x;  // periodic geometry: the outputs whose first tap is l are S*l + ph + m, m = 0..S-1
   double ph_dist_y[8][2], ph_dist_x[8][2];  // their distances to tap 0 / tap 1
 };
+
+// lut_cell.cu
+int build_cell_tables(lerf_luts_impl* L, const int8_t* const host_tables[9]);
+int launch_stage_cell(const lerf_luts_impl* L, int stage, const uint8_t* in, const InAddr& ia, int planes, int H, int W,
+                      int y0, int y1, uint8_t* out, int variant, cudaStream_t st);
 
 // resample_int.cu
 int resize_sr_int_gauss(const lerf_sr_plan_impl* P, const uint8_t* feat, const uint8_t* codes, int planes, int channels,

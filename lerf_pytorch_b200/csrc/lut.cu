@@ -210,95 +210,6 @@ __global__ void __launch_bounds__(kTX* kTY, (MINB >= 11 ? 3 : MINB))
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Stage 1, persistent variant: tables s and c live in shared memory (2 x 83.5 KB, staged once per CTA with one
-// TMA bulk copy each), table t stays on the L1/L2 path (the third table does not fit in 227 KB).  One CTA per SM
-// walks 32x32 tiles.  Table gathers then cost one LDS with no tag lookup and no long-scoreboard stall.
-// ---------------------------------------------------------------------------------------------
-constexpr int kS1Slot = (kEntries + 255) / 256 * 256;  // 83712: bytes per stage-1 table slot in the LUT block
-constexpr int kPT = 32;                                // persistent tile width
-constexpr int kPPitch = kPT + 2 * kHalo + 2;           // 40
-constexpr int kPTileBytesMax = (32 + 2 * kHalo) * kPPitch;
-
-__device__ __forceinline__ int blend1s(const int8_t* t, const Simplex& s) {  // shared-memory table
-  return s.w0 * (int)t[s.i0] + s.w1 * (int)t[s.i1] + s.w2 * (int)t[s.i2] + s.w3 * (int)t[s.i3] + s.w4 * (int)t[s.i4];
-}
-
-template <int MODE, int R>
-__device__ __forceinline__ Simplex simplex_at_p(const uint8_t* c) {
-  const int va = c[Tap<MODE, R, 0>::dy * kPPitch + Tap<MODE, R, 0>::dx];
-  const int vb = c[Tap<MODE, R, 1>::dy * kPPitch + Tap<MODE, R, 1>::dx];
-  const int vc = c[Tap<MODE, R, 2>::dy * kPPitch + Tap<MODE, R, 2>::dx];
-  const int vd = c[Tap<MODE, R, 3>::dy * kPPitch + Tap<MODE, R, 3>::dx];
-  return simplex_of(va, vb, vc, vd);
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-template <int PTY>  // tile height = warps per CTA (32: 1024 threads / 64 regs, 16: 512 threads / 128 regs)
-__global__ void __launch_bounds__(kPT* PTY, 1)
-    lut_stage1_smem_kernel(const int8_t* __restrict__ tab_sc, const int8_t* __restrict__ tab_t,
-                           const uint8_t* __restrict__ in, InAddr ia, int H, int W, int y0, int y1, int tiles_x,
-                           int tiles_y, int ntiles, uint8_t* __restrict__ out) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  int8_t* ts = reinterpret_cast<int8_t*>(smem);
-  int8_t* tc = ts + kS1Slot;
-  uint8_t* tile = smem + 2 * kS1Slot;
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(tile + (kPTileBytesMax + 15) / 16 * 16);
-  const int tid = threadIdx.y * kPT + threadIdx.x;
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (tid == 0) {  // TMA bulk copies (UBLKCP): both tables land in shared memory while the first tile is loaded
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(2 * kS1Slot) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(ts)),
-                 "l"(tab_sc), "r"(kS1Slot), "r"(smem_u32(mbar))
-                 : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(tc)),
-                 "l"(tab_sc + kS1Slot), "r"(kS1Slot), "r"(smem_u32(mbar))
-                 : "memory");
-  }
-  bool tables_ready = false;
-  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int p = t / (tiles_x * tiles_y);
-    const int rem = t - p * (tiles_x * tiles_y);
-    const int tyi = rem / tiles_x, txi = rem - tyi * tiles_x;
-    const int bx = txi * kPT, by = y0 + tyi * PTY;
-    const uint8_t* src = in + (long long)(p / ia.channels) * ia.batch_stride + (long long)(p % ia.channels) * ia.chan_stride;
-    __syncthreads();  // previous tile fully consumed
-    for (int i = tid; i < (PTY + 2 * kHalo) * (kPT + 2 * kHalo); i += kPT * PTY) {
-      const int r = i / (kPT + 2 * kHalo), c = i - r * (kPT + 2 * kHalo);
-      const int gy = clampi(by + r - kHalo, 0, H - 1), gx = clampi(bx + c - kHalo, 0, W - 1);
-      tile[r * kPPitch + c] = __ldg(src + (long long)gy * ia.row_stride + (long long)gx * ia.pix_stride);
-    }
-    if (!tables_ready) {
-      uint32_t done = 0;
-      while (!done)
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
-                     : "=r"(done) : "r"(smem_u32(mbar)) : "memory");
-      tables_ready = true;
-    }
-    __syncthreads();
-    const int x = bx + threadIdx.x, y = by + threadIdx.y;
-    if (x < W && y < y1) {
-      const uint8_t* c = tile + (threadIdx.y + kHalo) * kPPitch + threadIdx.x + kHalo;
-      int n = 0;
-#define LERF_SS(M, R) n += blend1s(M == 0 ? ts : tc, simplex_at_p<M, R>(c));
-      LERF_SS(0, 0) LERF_SS(0, 1) LERF_SS(0, 2) LERF_SS(0, 3)
-      LERF_SS(1, 0) LERF_SS(1, 1) LERF_SS(1, 2) LERF_SS(1, 3)
-#undef LERF_SS
-      n += blend1(tab_t, simplex_at_p<2, 0>(c));
-      n += blend1(tab_t, simplex_at_p<2, 1>(c));
-      n += blend1(tab_t, simplex_at_p<2, 2>(c));
-      n += blend1(tab_t, simplex_at_p<2, 3>(c));
-      const int v = n <= 0 ? 0 : min(rhe_div(n, 48), 255);
-      out[((long long)p * H + y) * W + x] = (uint8_t)v;
-    }
-  }
-}
-
 // Generic single pass (any of the five modes, any oC): the drop-in for one call of
 // FourSimplexInterpFaster.  Slow path by design -- the product path uses the stage kernels.
 struct PassTaps {
@@ -348,7 +259,7 @@ static bool mode_taps(char mode, PassTaps& t, int& pad) {
 
 using namespace lerf;
 
-static int g_stage1_variant = 0, g_stage2_variant = 0;
+static int g_lut_variant[2] = {0, 0};  // per stage: 0 = production, 1..19 legacy row-major kernel, 20+ cell kernel
 
 extern "C" {
 
@@ -384,6 +295,7 @@ int lerf_luts_create(const int8_t* const host_tables[9], int oC2, int device, le
     }
   }
   lerf_luts_impl* L = new lerf_luts_impl();
+  memset(L, 0, sizeof(*L));
   L->device = device;
   L->oC2 = oC2;
   L->block_bytes = total;
@@ -402,8 +314,15 @@ int lerf_luts_create(const int8_t* const host_tables[9], int oC2, int device, le
   }
   for (int i = 0; i < 3; ++i) L->s1[i] = (const int8_t*)((uint8_t*)L->block + i * s1_bytes);
   for (int i = 0; i < 6; ++i) L->s2[i] = (uint8_t*)L->block + 3 * s1_bytes + i * s2_bytes;
-  // Reserve persisting L2 for the block (best effort; the window itself is per stream).
-  size_t want = total;
+  int rc = build_cell_tables(L, host_tables);
+  if (rc) {
+    cudaFree(L->cell_block);
+    cudaFree(L->block);
+    delete L;
+    return rc;
+  }
+  // Reserve persisting L2 for the tables (best effort; the window itself is per stream).
+  size_t want = L->cell_block_bytes;
   cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
   cudaGetLastError();
   *out = reinterpret_cast<lerf_luts_t*>(L);
@@ -415,6 +334,7 @@ void lerf_luts_destroy(lerf_luts_t* luts) {
   lerf_luts_impl* L = reinterpret_cast<lerf_luts_impl*>(luts);
   cudaSetDevice(L->device);
   cudaFree(L->block);
+  cudaFree(L->cell_block);
   delete L;
 }
 
@@ -427,8 +347,8 @@ int lerf_luts_pin_l2(const lerf_luts_t* luts, lerf_stream_t stream) {
   const lerf_luts_impl* L = reinterpret_cast<const lerf_luts_impl*>(luts);
   cudaStreamAttrValue attr;
   memset(&attr, 0, sizeof(attr));
-  attr.accessPolicyWindow.base_ptr = L->block;
-  attr.accessPolicyWindow.num_bytes = L->block_bytes;
+  attr.accessPolicyWindow.base_ptr = L->cell_block;  // the tables the production kernels read
+  attr.accessPolicyWindow.num_bytes = L->cell_block_bytes;
   attr.accessPolicyWindow.hitRatio = 1.0f;
   attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
   attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
@@ -472,36 +392,12 @@ int lerf_lut_stage1(const lerf_luts_t* luts, const uint8_t* in, int planes, int 
   for (int i = 0; i < 3; ++i) t.t[i] = L->s1[i];
   for (int i = 3; i < 6; ++i) t.t[i] = nullptr;
   InAddr ia{in_channels, in_batch_stride, in_chan_stride, in_row_stride, in_pix_stride};
-  // Large inputs: persistent kernel with tables s and c in shared memory; small ones: the L1-path kernel.
-  const int pty = g_stage1_variant == 3 ? 16 : 32;
-  const int tiles_x = (W + kPT - 1) / kPT, tiles_y = (y1 - y0 + pty - 1) / pty;
-  const long long ntiles = (long long)tiles_x * tiles_y * planes;
-  if ((g_stage1_variant == 2 || g_stage1_variant == 3) && ntiles < (1LL << 31) &&
-      L->s1[1] == L->s1[0] + kS1Slot) {
-    const int smem_bytes = 2 * kS1Slot + (kPTileBytesMax + 15) / 16 * 16 + 16;
-    static thread_local int attr_dev = -1;
-    if (attr_dev != L->device) {
-      LERF_CUDA(cudaFuncSetAttribute(lut_stage1_smem_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-      LERF_CUDA(cudaFuncSetAttribute(lut_stage1_smem_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-      attr_dev = L->device;
-    }
-    const int grid = (int)(ntiles < L->num_sms ? ntiles : L->num_sms);
-    if (pty == 32)
-      lut_stage1_smem_kernel<32><<<grid, dim3(kPT, 32), smem_bytes, (cudaStream_t)stream>>>(
-          L->s1[0], L->s1[2], in, ia, H, W, y0, y1, tiles_x, tiles_y, (int)ntiles, feat);
-    else
-      lut_stage1_smem_kernel<16><<<grid, dim3(kPT, 16), smem_bytes, (cudaStream_t)stream>>>(
-          L->s1[0], L->s1[2], in, ia, H, W, y0, y1, tiles_x, tiles_y, (int)ntiles, feat);
-    LERF_LAUNCHED();
-    return LERF_OK;
-  }
+  if (g_lut_variant[0] == 0 || g_lut_variant[0] >= 20)  // production: cell-packed tables (lut_cell.cu)
+    return launch_stage_cell(L, 1, in, ia, planes, H, W, y0, y1, feat, g_lut_variant[0] >= 20 ? g_lut_variant[0] - 20 : 0,
+                             (cudaStream_t)stream);
   dim3 block(kTX, kTY), grid((W + kTX - 1) / kTX, (y1 - y0 + kTY - 1) / kTY, planes);
-  switch (g_stage1_variant) {
+  switch (g_lut_variant[0]) {  // legacy row-major-table kernel (kept for A/B timing and as a second implementation)
     case 4: lut_stage_kernel<1, 1, 4><<<grid, block, 0, (cudaStream_t)stream>>>(t, in, ia, H, W, y0, y1, feat); break;
-    case 5: lut_stage_kernel<1, 1, 5><<<grid, block, 0, (cudaStream_t)stream>>>(t, in, ia, H, W, y0, y1, feat); break;
-    case 6: lut_stage_kernel<1, 1, 6><<<grid, block, 0, (cudaStream_t)stream>>>(t, in, ia, H, W, y0, y1, feat); break;
-    case 8: lut_stage_kernel<1, 1, 8><<<grid, block, 0, (cudaStream_t)stream>>>(t, in, ia, H, W, y0, y1, feat); break;
-    case 3 + 100: lut_stage_kernel<1, 1, 3><<<grid, block, 0, (cudaStream_t)stream>>>(t, in, ia, H, W, y0, y1, feat); break;
     case 11: lut_stage_kernel<1, 1, 11><<<grid, block, 0, (cudaStream_t)stream>>>(t, in, ia, H, W, y0, y1, feat); break;
     case 12: lut_stage_kernel<1, 1, 12><<<grid, block, 0, (cudaStream_t)stream>>>(t, in, ia, H, W, y0, y1, feat); break;
     default: lut_stage_kernel<1, 1, 3><<<grid, block, 0, (cudaStream_t)stream>>>(t, in, ia, H, W, y0, y1, feat);
@@ -510,10 +406,9 @@ int lerf_lut_stage1(const lerf_luts_t* luts, const uint8_t* in, int planes, int 
   return LERF_OK;
 }
 
-/* Testing / tuning hook: 0 = choose by size, 1 = always the L1-path kernel, 2 = always the shared-memory kernel. */
-void lerf_debug_stage1_variant(int v) {
-  g_stage1_variant = v % 100;
-  g_stage2_variant = v / 100;
+/* Testing / tuning hook (see lerf_b200.h). */
+void lerf_debug_lut_variant(int stage, int variant) {
+  if (stage == 1 || stage == 2) g_lut_variant[stage - 1] = variant;
 }
 
 int lerf_lut_stage2(const lerf_luts_t* luts, const uint8_t* feat, int planes, int H, int W, int y0, int y1,
@@ -525,13 +420,13 @@ int lerf_lut_stage2(const lerf_luts_t* luts, const uint8_t* feat, int planes, in
   StageTables t;
   for (int i = 0; i < 6; ++i) t.t[i] = L->s2[i];
   InAddr ia{1, (long long)H * W, 0, W, 1};
+  if (g_lut_variant[1] == 0 || g_lut_variant[1] >= 20)
+    return launch_stage_cell(L, 2, feat, ia, planes, H, W, y0, y1, codes, g_lut_variant[1] >= 20 ? g_lut_variant[1] - 20 : 0,
+                             (cudaStream_t)stream);
   dim3 block(kTX, kTY), grid((W + kTX - 1) / kTX, (y1 - y0 + kTY - 1) / kTY, planes);
   if (L->oC2 == 3) {
-    switch (g_stage2_variant) {
+    switch (g_lut_variant[1]) {
       case 3: lut_stage_kernel<2, 3, 3><<<grid, block, 0, (cudaStream_t)stream>>>(t, feat, ia, H, W, y0, y1, codes); break;
-      case 1: lut_stage_kernel<2, 3, 1><<<grid, block, 0, (cudaStream_t)stream>>>(t, feat, ia, H, W, y0, y1, codes); break;
-      case 5: lut_stage_kernel<2, 3, 5><<<grid, block, 0, (cudaStream_t)stream>>>(t, feat, ia, H, W, y0, y1, codes); break;
-      case 8: lut_stage_kernel<2, 3, 8><<<grid, block, 0, (cudaStream_t)stream>>>(t, feat, ia, H, W, y0, y1, codes); break;
       default: lut_stage_kernel<2, 3, 4><<<grid, block, 0, (cudaStream_t)stream>>>(t, feat, ia, H, W, y0, y1, codes);
     }
   } else {

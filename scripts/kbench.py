@@ -38,23 +38,24 @@ def timeit(fn):
 for kind in os.environ.get("KB_KINDS", "natural,uniform").split(","):
     frames = (bench.natural_frames_gpu if kind == "natural" else bench.uniform_frames_gpu)(B, 3000, dev)
     ref_feat = None
-    s1_variants = ((0, "L1-path minb3"), (2, "smem 32x32/1024thr"), (3, "smem 32x16/512thr"), (4, "L1 minb4"),
-                   (11, "EXP same-address loads"), (12, "EXP no loads"))
+    s1_variants = ((0, "cell (production)"), (1, "row-major minb3"), (22, "cell minb2"), (23, "cell minb3"),
+                   (25, "cell minb5"), (26, "cell minb6"), (11, "row-major EXP same-addr"), (12, "row-major EXP no loads"))
     for v, name in (s1_variants[:1] if ONLY == "prod" else s1_variants):
-        L.lerf_debug_stage1_variant(v)
+        L.lerf_debug_lut_variant(1, v)
         feat = lp.lut_stage1(luts, frames)
         if ref_feat is None:
             ref_feat = feat.clone()
-        assert v >= 11 or torch.equal(feat, ref_feat), "stage-1 variants disagree"
-        print("%-8s stage1 %-20s %8.1f us/frame" % (kind, name, timeit(lambda: lp.lut_stage1(luts, frames, out=feat))), flush=True)
-    L.lerf_debug_stage1_variant(0)
+        assert v in (11, 12) or torch.equal(feat, ref_feat), "stage-1 variants disagree"
+        print("%-8s stage1 %-24s %8.1f us/frame" % (kind, name, timeit(lambda: lp.lut_stage1(luts, frames, out=feat))), flush=True)
+    L.lerf_debug_lut_variant(1, 0)
     codes = lp.lut_stage2(luts, ref_feat)
-    for v in ((0,) if ONLY == "prod" else (0, 1, 3, 5)):
-        L.lerf_debug_stage1_variant(100 * v)
+    s2_variants = ((0, "cell (production)"), (1, "row-major minb4"), (22, "cell minb2"), (23, "cell minb3"), (25, "cell minb5"))
+    for v, name in (s2_variants[:1] if ONLY == "prod" else s2_variants):
+        L.lerf_debug_lut_variant(2, v)
         c2 = lp.lut_stage2(luts, ref_feat)
-        assert torch.equal(c2, codes)
-        print("%-8s stage2 %-20s %8.1f us/frame" % (kind, "minb%d" % v, timeit(lambda: lp.lut_stage2(luts, ref_feat, out=c2))), flush=True)
-    L.lerf_debug_stage1_variant(0)
+        assert torch.equal(c2, codes), "stage-2 variants disagree"
+        print("%-8s stage2 %-24s %8.1f us/frame" % (kind, name, timeit(lambda: lp.lut_stage2(luts, ref_feat, out=c2))), flush=True)
+    L.lerf_debug_lut_variant(2, 0)
     rs = lp.SteeringGaussianResize2d(support_sz=2, max_sigma=10)
     rs.set_shape([3, bench.H, bench.W], scale_factors=[4, 4])
     for fmt in ("f32", "u8", "u8_hwc"):

@@ -1,0 +1,72 @@
+// CPU emulation of the cell-packed LUT lookup (lerf_pytorch_b200/csrc/lut_cell.cuh) -- TEST INFRASTRUCTURE ONLY.
+// It compiles the product's own header with g++ (every device intrinsic has a host twin there) and walks an
+// image exactly like lut_stage_cell_kernel does, so the bit tricks (key layout, PRMT selectors, byte weights, table
+// repack) are checked against the oracle on the CPU before any GPU time is spent.  Nothing in the product loads it.
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../lerf_pytorch_b200/csrc/lut_cell.cuh"
+
+using namespace lerf::cell;
+
+static void tap_offset(int mode, int r, int k, int& dy, int& dx) {  // mode 0='s',1='c',2='t' (eval_lut_sr.py:30-81)
+  const int di = mode == 0 ? (k >> 1) : (mode == 1 ? 0 : k);
+  const int dj = mode == 0 ? (k & 1) : k;
+  dy = r == 0 ? di : (r == 1 ? dj : (r == 2 ? -di : -dj));
+  dx = r == 0 ? dj : (r == 1 ? -di : (r == 2 ? -dj : di));
+}
+
+static int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+static int rhe_div(int num, int den) {
+  const int t = num + den / 2;
+  int q = t / den;
+  if (t - q * den == 0 && (q & 1)) --q;
+  return q;
+}
+
+extern "C" int emul_stage_cell(int stage, const int8_t* const* tables, int oC, const uint8_t* img, int P, int H, int W,
+                               uint8_t* out) {
+  const int ntab = stage == 1 ? 3 : 6;
+  const size_t stride = oC == 3 ? 64 : 16;
+  std::vector<std::vector<uint8_t>> packed(ntab);
+  const int ident[4] = {0, 1, 2, 3};
+  for (int i = 0; i < ntab; ++i) {
+    packed[i].assign((size_t)65536 * stride, 0);
+    repack_cells(tables[i], oC, ident, packed[i].data(), stride, 0);
+  }
+  for (int p = 0; p < P; ++p)
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) {
+        int n[3] = {0, 0, 0};
+        for (int mode = 0; mode < 3; ++mode)
+          for (int r = 0; r < 4; ++r) {
+            uint32_t xw[4];
+            for (int k = 0; k < 4; ++k) {
+              int dy, dx;
+              tap_offset(mode, r, k, dy, dx);
+              xw[k] = split_px(img[((size_t)p * H + clampi(y + dy, 0, H - 1)) * W + clampi(x + dx, 0, W - 1)]);
+            }
+            const Simplex s = simplex_of(xw[0], xw[1], xw[2], xw[3]);
+            const uint8_t* tab = packed[stage == 1 ? mode : 2 * mode + (r & 1)].data() + (size_t)s.cell * stride;
+            for (int ch = 0; ch < oC; ++ch) {
+              uint32_t q[4];
+              memcpy(q, tab + 16 * ch, 16);
+              n[ch] += blend(q[0], q[1], q[2], q[3], s);
+            }
+          }
+        for (int ch = 0; ch < oC; ++ch) {
+          int v;
+          if (stage == 1) {
+            v = n[ch] <= 0 ? 0 : (rhe_div(n[ch], 48) > 255 ? 255 : rhe_div(n[ch], 48));
+          } else {
+            const int t = n[ch] + 127 * 192;
+            v = t <= 0 ? 0 : (rhe_div(t, 192) > 255 ? 255 : rhe_div(t, 192));
+          }
+          out[(((size_t)p * oC + ch) * H + y) * W + x] = (uint8_t)v;
+        }
+      }
+  return 0;
+}

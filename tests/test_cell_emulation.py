@@ -1,0 +1,57 @@
+"""CPU check of the cell-packed LUT lookup's bit tricks: the product header lut_cell.cuh is compiled with g++
+(host twins of prmt / dp4a) and run over images exactly like the kernel; results must equal the oracle's."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import lerf_oracle as orc
+import util
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "csrc", "cell_emul.cpp")
+LIB = os.path.join(HERE, "csrc", "libcell_emul.so")
+HDR = os.path.join(os.path.dirname(HERE), "lerf_pytorch_b200", "csrc", "lut_cell.cuh")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
+        gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        env = dict(os.environ)
+        env.pop("CC", None)
+        env.pop("CXX", None)
+        subprocess.check_call([gxx, "-O2", "-fPIC", "-shared", "-std=c++17", "-x", "c++", SRC, "-o", LIB], env=env)
+    return ctypes.CDLL(LIB)
+
+
+def _run(emul, stage, tables, oC, img_chw):
+    P, H, W = img_chw.shape
+    tabs = [np.ascontiguousarray(t, dtype=np.int8) for t in tables]
+    arr = (ctypes.c_void_p * len(tabs))(*[t.ctypes.data for t in tabs])
+    out = np.empty((P * oC, H, W), dtype=np.uint8)
+    img = np.ascontiguousarray(img_chw, dtype=np.uint8)
+    assert emul.emul_stage_cell(stage, arr, oC, ctypes.c_void_p(img.ctypes.data), P, H, W, ctypes.c_void_p(out.ctypes.data)) == 0
+    return out
+
+
+@pytest.mark.parametrize("oC,kind", [(3, "shipped"), (1, "shipped"), (3, "random"), (1, "random")])
+def test_cell_lookup_equals_oracle(emul, oC, kind):
+    if kind == "shipped":
+        luts = orc.load_luts(util.lut_dir("lerf-g" if oC == 3 else "lerf-l"), linear=(oC == 1))
+    else:
+        luts = util.random_luts(11 + oC, oC2=oC)  # full int8 range incl. -128
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, size=(37, 29, 3)).astype(np.uint8)
+    img[:6, :6] = 255  # msb 15 / lsb 15 corner: vertex rows at index 16
+    img[6:10, :8] = (np.arange(8) * 16)[None, :, None]  # all-lsb-zero ties
+    feat, codes, _ = orc.lut_stages(img, luts, oC=oC)
+    chw = np.ascontiguousarray(np.transpose(img, (2, 0, 1)))
+    t1 = [luts["s1_%sr0" % m] for m in "sct"]
+    t2 = []
+    for m in "sct":
+        t2 += [luts["s2_%sr0" % m], luts["s2_%sr1" % m]]
+    assert np.array_equal(_run(emul, 1, t1, 1, chw), feat)
+    assert np.array_equal(_run(emul, 2, t2, oC, feat), codes)

@@ -107,6 +107,29 @@ def test_stages_full_range_random_luts_vs_oracle(lp, orc, oC):
         assert np.array_equal(codes[3 * oC * b:3 * oC * (b + 1)].cpu().numpy(), rc), b
 
 
+@pytest.mark.parametrize("oC", [1, 3])
+def test_stage_kernel_variants_are_bitwise_identical(lp, oC):
+    """Two independent implementations (row-major-table kernel, cell-packed-table kernel and its tuning variants)
+    must produce the same bytes on full-range inputs and tables."""
+    ld = random_luts(23 + oC, oC2=oC)
+    ls = lp.LutSet(ld, linear=(oC == 1))
+    img = _cuda(uniform_image(91, 75, 131))
+    L = lp.lib()
+    try:
+        ref = None
+        for v in (0, 1, 22, 23, 25):
+            L.lerf_debug_lut_variant(1, v)
+            L.lerf_debug_lut_variant(2, v)
+            feat = lp.lut_stage1(ls, img)
+            codes = lp.lut_stage2(ls, feat)
+            if ref is None:
+                ref = (feat.clone(), codes.clone())
+            assert torch.equal(feat, ref[0]) and torch.equal(codes, ref[1]), v
+    finally:
+        L.lerf_debug_lut_variant(1, 0)
+        L.lerf_debug_lut_variant(2, 0)
+
+
 def test_stage_row_bands_equal_full(lp, luts):
     _, ls = luts["g"]
     img = _cuda(uniform_image(77, 61, 53))
