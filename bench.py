@@ -366,7 +366,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "MPix/s", "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int32 LUT stages; f64 exponent + f32 ex2 + f64 accumulate resampling",
+            "vs_baseline": None, "dtype": "int32 LUT stages (dp4a on int8 tables); f64 exponent + f32 ex2/accumulate resampling",
             "data": "synthetic",
             "config": {"workload": "cfg-3: LeRF-G LUT x4 SR of synthetic 2040x1356 frames, uint8 in -> float32 planar out",
                        "frames_per_gpu_per_step": B, "input": args.input, "sharding": "per image, no collective",

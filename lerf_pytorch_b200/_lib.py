@@ -29,7 +29,9 @@ PROTOTYPES = {
     "lerf_sr_plan_destroy": (None, [_c_p]),
     "lerf_resize_sr": (_c_i, [_c_i, _c_p, _c_p, _c_p, _c_i, _c_i, _c_f, _c_i, _c_i, _c_p, _c_i, _c_p]),
     "lerf_debug_force_generic": (None, [_c_i]),
+    "lerf_debug_resize_variant": (None, [_c_i]),
     "lerf_debug_lut_variant": (None, [_c_i, _c_i]),
+    "lerf_debug_cell_hash": (None, [_c_i, _c_i, _c_i]),
     "lerf_resize_sr_f32": (_c_i, [_c_i, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_f, _c_p, _c_p]),
     "lerf_warp": (_c_i, [_c_i, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p, _c_i, _c_i, _c_f, _c_p, _c_i,
                          _c_p, _c_i, _c_i, _c_i, _c_p]),
@@ -38,6 +40,7 @@ PROTOTYPES = {
     "lerf_sr_scratch_bytes": (_c_sz, [_c_i, _c_i, _c_i, _c_i]),
     "lerf_sr_fused": (_c_i, [_c_p, _c_i, _c_p, _c_p, _c_i, _c_i, _c_ll, _c_ll, _c_ll, _c_ll, _c_f, _c_i, _c_i, _c_p,
                              _c_p, _c_i, _c_p]),
+    "lerf_debug_pipeline": (None, [_c_i, _c_i, _c_i]),
     "lerf_launch_count": (_c_ll, []),
     "lerf_launch_count_reset": (None, []),
 }

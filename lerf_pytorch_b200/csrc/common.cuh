@@ -58,6 +58,7 @@ struct lerf_luts_impl {
   // channel k at [16k, 16k+16))
   void* cell_block;
   size_t cell_block_bytes;
+  int cell_hash[3];  // block swizzle weights (lut_cell.cuh), fixed when the set is created
   const uint8_t* c1[3];
   const uint8_t* c2[6];
 };
@@ -80,8 +81,18 @@ int build_cell_tables(lerf_luts_impl* L, const int8_t* const host_tables[9]);
 int launch_stage_cell(const lerf_luts_impl* L, int stage, const uint8_t* in, const InAddr& ia, int planes, int H, int W,
                       int y0, int y1, uint8_t* out, int variant, cudaStream_t st);
 
+int launch_stage2_mix(const lerf_luts_impl* L, const uint8_t* feat, int planes, int H, int W, int y0, int y1, uint8_t* out,
+                      int variant, cudaStream_t st);
+
+// pipeline.cu
+int sr_pipeline(const lerf_luts_impl* L, int kind, const lerf_sr_plan_impl* P, const uint8_t* in, int planes, const InAddr& ia,
+                float max_sigma, int oy0, int oy1, uint8_t* feat, uint8_t* codes, void* out, int fmt, cudaStream_t st);
+void sr_pipeline_config(int enabled, int minb, int group_planes);
+
 // resample_int.cu
 int resize_sr_int_gauss(const lerf_sr_plan_impl* P, const uint8_t* feat, const uint8_t* codes, int planes, int channels,
                         float max_sigma, int oy0, int oy1, void* out, int fmt, cudaStream_t st);
+
+void resize_int_config(int variant);
 
 }  // namespace lerf

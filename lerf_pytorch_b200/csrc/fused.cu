@@ -33,12 +33,20 @@ int lerf_sr_fused(const lerf_luts_t* luts, int kind, const lerf_sr_plan_t* plan,
   const int f0 = clampr(c0 - 3), f1 = clampr(c1 + 3);
   uint8_t* feat = (uint8_t*)scratch;
   uint8_t* codes = feat + ((size_t)planes * H * W + 255) / 256 * 256;
-  int rc = lerf_lut_stage1(luts, in, planes, H, W, in_channels, in_batch_stride, in_chan_stride, in_row_stride,
+  if (in_channels < 1 || (planes % in_channels)) return fail(LERF_EINVAL, "lerf_sr_fused: planes=%d not a multiple of in_channels=%d", planes, in_channels);
+  // Batches: the role-interleaved pipeline kernel (pipeline.cu) overlaps the three steps on different plane groups.
+  const InAddr ia{in_channels, in_batch_stride, in_chan_stride, in_row_stride, in_pix_stride};
+  int rc = sr_pipeline(L, kind, P, in, planes, ia, max_sigma, oy0, oy1, feat, codes, out, out_format, (cudaStream_t)stream);
+  if (rc != -1) return rc;
+  rc = lerf_lut_stage1(luts, in, planes, H, W, in_channels, in_batch_stride, in_chan_stride, in_row_stride,
                            in_pix_stride, f0, f1 + 1, feat, stream);
   if (rc) return rc;
   rc = lerf_lut_stage2(luts, feat, planes, H, W, c0, c1 + 1, codes, stream);
   if (rc) return rc;
   return lerf_resize_sr(kind, plan, feat, codes, planes, in_channels, max_sigma, oy0, oy1, out, out_format, stream);
 }
+
+/* Testing / tuning hook (see lerf_b200.h). */
+void lerf_debug_pipeline(int enabled, int min_blocks, int group_planes) { sr_pipeline_config(enabled, min_blocks, group_planes); }
 
 }  // extern "C"

@@ -69,12 +69,28 @@ struct Simplex {
   uint32_t wX, wY;      // byte weights matching the PRMT results:  [w1, w3, 0, 0] and [w2, w4, 0, w0]
 };
 
+// Block swizzle.  A 128-bit load is served in groups of 8 lanes; two lanes of a group that read different 128-byte
+// lines at the same 16-byte slot collide in the L1 data banks.  Neighbouring pixels often share msb_d (the slot
+// of the plain layout) while differing in the other msbs, which made every lookup ~4-way conflicted (ncu, r1c).
+// The block of cell (a,b,c,d) is therefore stored at (cell & ~15) | ((d + ha*a + hb*b + hc*c) & 15): with odd
+// weights every single-coordinate step, and every step along the diagonal, changes the slot.
+struct Hash {
+  uint32_t ha, hb, hc;  // 0,0,0 = plain layout
+};
+
+LERF_HD uint32_t swizzled_cell(uint32_t cellidx, const Hash& h) {
+  const uint32_t a = (cellidx >> 12) & 15u, b = (cellidx >> 8) & 15u, c = (cellidx >> 4) & 15u, d = cellidx & 15u;
+  return (cellidx & ~15u) | ((d + h.ha * a + h.hb * b + h.hc * c) & 15u);
+}
+
 // Taps a, b, c, d (split_px words) in table-axis order.
-LERF_HD Simplex simplex_of(uint32_t xa, uint32_t xb, uint32_t xc, uint32_t xd) {
+LERF_HD Simplex simplex_of(uint32_t xa, uint32_t xb, uint32_t xc, uint32_t xd, const Hash& h) {
   Simplex s;
   // msb fields land in bits 8..23; the lsb bytes only reach bits >= 24 (or overflow out).
   const uint32_t acc = ((xa * 16u + xb) * 16u + xc) * 16u + xd;
-  s.cell = prmt(acc, 0u, 0x4421u);
+  // bits 8..11 of acc + ha*xa + hb*xb + hc*xc = (d + ha*a + hb*b + hc*c) mod 16: the X words are zero below bit 8
+  const uint32_t mix = xa * h.ha + (xb * h.hb + (xc * h.hc + acc));
+  s.cell = prmt((acc & ~0xF00u) | (mix & 0xF00u), 0u, 0x4421u);
   // key = lsb<<24 | msb<<8 | (tap's corner bit & 7) replicated in nibbles 0 and 1.  Sorting descending orders the
   // taps by lsb (ties: any order, the tied vertices get weight 0).
   int k1 = (int)(xa | 0x00u), k2 = (int)(xb | 0x44u), k3 = (int)(xc | 0x22u), k4 = (int)(xd | 0x11u);
@@ -111,18 +127,20 @@ LERF_HD int corner_pos(int m) {
 }
 
 // Host-side repack of one row-major table T[17^4][oC] (int8) into cell blocks.
-//   dst[cell * cell_stride + slot_off + ch * 16 + corner_pos(m)] = T[perm-ed row][ch]
+//   dst[swizzled_cell(cell) * cell_stride + slot_off + ch * 16 + corner_pos(m)] = T[perm-ed row][ch]
 // perm[k] = which of the lookup's taps (0=a..3=d, in the order the kernel passes them) feeds table axis k, so a
 // kernel that passes taps in ANCHOR order (A,B,C,D) reads the value T[tap perm[0], tap perm[1], ...].
-inline void repack_cells(const int8_t* T, int oC, const int perm[4], uint8_t* dst, size_t cell_stride, size_t slot_off) {
+inline void repack_cells(const int8_t* T, int oC, const int perm[4], const Hash& h, uint8_t* dst, size_t cell_stride,
+                         size_t slot_off) {
   for (int cellidx = 0; cellidx < 65536; ++cellidx) {
+    const size_t block = swizzled_cell((uint32_t)cellidx, h);
     const int msb[4] = {(cellidx >> 12) & 15, (cellidx >> 8) & 15, (cellidx >> 4) & 15, cellidx & 15};
     for (int m = 0; m < 16; ++m) {
       const int bump[4] = {(m >> 3) & 1, (m >> 2) & 1, (m >> 1) & 1, m & 1};
       int row = 0;
       for (int k = 0; k < 4; ++k) row = row * 17 + msb[perm[k]] + bump[perm[k]];
       for (int ch = 0; ch < oC; ++ch)
-        dst[(size_t)cellidx * cell_stride + slot_off + (size_t)ch * 16 + corner_pos(m)] = (uint8_t)T[(size_t)row * oC + ch];
+        dst[block * cell_stride + slot_off + (size_t)ch * 16 + corner_pos(m)] = (uint8_t)T[(size_t)row * oC + ch];
     }
   }
 }

@@ -410,6 +410,9 @@ int lerf_resize_sr(int kind, const lerf_sr_plan_t* plan, const uint8_t* feat, co
 /* Testing hook: route integer scales through the generic kernel too (parity tests compare both). */
 void lerf_debug_force_generic(int on) { g_force_generic = on != 0; }
 
+/* Testing / tuning hook for the integer-scale kernel (see lerf_b200.h). */
+void lerf_debug_resize_variant(int variant) { resize_int_config(variant); }
+
 int lerf_resize_sr_f32(int kind, const lerf_sr_plan_t* plan, const float* img, const float* h0, const float* h1,
                        const float* h2, int planes, float max_sigma, float* out, lerf_stream_t stream) {
   const lerf_sr_plan_impl* P = reinterpret_cast<const lerf_sr_plan_impl*>(plan);

@@ -1,0 +1,234 @@
+// Integer-scale specialisation of the LeRF-G SR resampler (S = 2, 3, 4, 8 on both axes, out = S * in): device body
+// shared by the plain kernel in resample_int.cu and the pipeline kernel in pipeline.cu.
+// Replaces SteeringGaussianResize2dNumpy.resize (resize_right/resize_right2d_numpy.py:162-223 of the reference)
+// for the configurations where the geometry is periodic (BASELINE.json cfg-1, -3, -5).
+//
+// Design.  For an integer scale the S x S output pixels whose first tap is input pixel (ly, lx) share the same
+// 2x2 taps, so one thread owns one such CELL: it reads the four taps' coefficients once and produces S*S outputs.
+// Per tap pixel and plane the exponent is a quadratic form
+//     log2(w) = a' dr^2 + b' dr dc + c' dc^2,   a' = -L/2 sx^2,  b' = L rho sx sy,  c' = -L/2 sy^2,  L = log2(e)
+// whose coefficients are computed once per input sample in float64 from the reference's float32 hyper values (a
+// block stages them in shared memory), and whose geometry factors are float64 kernel-parameter constants.
+// HOIST variant: the column term c' dc^2 (+ the rounding constant) is hoisted per cell and the row terms a' dr^2,
+// b' dr per output row, so an exponent costs 2 FP64 ops instead of 4 -- but 80+ registers; measured no faster
+// than the plain form at 48 registers, which is the default.  Adding 1.5*2^(52-FB) leaves round(log2(w) * 2^FB) in the low word
+// of the double: the max over the four taps and the subtraction are then exact INTEGER ops, and only the difference
+// (<= 0) is converted to fp32 for ex2.approx -- the fp32 error stays in the low bits of weights that matter.  The
+// output is v00 + sum w_t (v_t - v00) / sum w_t with exact integer differences, so fp32 rounding scales with the
+// local contrast, not with 255.
+#pragma once
+#include "common.cuh"
+
+namespace lerf {
+namespace rsi {
+
+constexpr double kLog2e = 1.4426950408889634;
+
+template <int S>
+struct IntGeom {
+  double xr[S][2];        // dr^2       [row phase][tap b]
+  double xc[S][2];        // dc^2       [col phase][tap a]
+  double dr[S][2];        // dr
+  double dc[S][2];        // dc
+  double pp[S][S][2][2];  // dr * dc    [row phase][col phase][b][a]   (S = 8 form)
+  double magic;           // 1.5 * 2^(52 - FB)
+  float inv_scale;        // 2^-FB
+  int ph_y, ph_x;         // first output of cell l is S*l + ph
+};
+
+constexpr int kCX = 32, kCY = 8;  // cells per block
+
+struct CoefTabs {           // per-code float64 tables, exact promotions of the reference's float32 values
+  double s2[256];           // -L/2 * sigma^2
+  double sg[256];           // sigma
+  double rl[256];           // L * rho
+};
+
+struct Smem {
+  CoefTabs tab;
+  double sA[kCY + 1][kCX + 1], sB[kCY + 1][kCX + 1], sC[kCY + 1][kCX + 1];
+  float sV[kCY + 1][kCX + 1];
+};
+
+template <int FMT>
+__device__ __forceinline__ void store1(void* out, long long ip, long long ih, float val) {
+  if (FMT == LERF_OUT_F32) {
+    __stcg((float*)out + ip, val);
+  } else {
+    int q = __float2int_rn(val);  // round half to even
+    q = min(max(q, 0), 255);
+    __stcg((uint8_t*)out + (FMT == LERF_OUT_U8 ? ip : ih), (uint8_t)q);
+  }
+}
+
+// 4 fixed-point exponents (round(log2 w * 2^FB)) and the 4 tap differences -> one output sample.
+// (Building 2^x without the int->float conversion -- mantissa bits + exponent-field add -- was measured SLOWER: the
+// kernel is issue-bound and that form needs one more instruction per tap)
+__device__ __forceinline__ float combine_q(const int q[4], const float dv[4], float v0, float inv_scale) {
+  const int qm = max(max(q[0], q[1]), max(q[2], q[3]));
+  float w[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float x = (float)(q[t] - qm) * inv_scale;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w[t]) : "f"(x));
+  }
+  const float den = (w[0] + w[1]) + (w[2] + w[3]);  // in [1, 4]: the max tap has weight 1
+  const float num = fmaf(w[1], dv[1], fmaf(w[2], dv[2], w[3] * dv[3]));
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
+  float qn = num * r;
+  qn = fmaf(fmaf(-den, qn, num), r, qn);  // residual correction with the approximate reciprocal: ~0.5 ulp quotient
+  return v0 + qn;
+}
+
+// Streaming traffic (codes, feat, outputs) uses .cg loads/stores: it must not evict the LUT lines that the stage
+// roles of the pipeline kernel keep in L1.
+// (bxi, byi, p): the block's cell-tile column, cell-tile row and plane; 256 threads.
+template <int S, int FMT, bool HOIST>
+__device__ __forceinline__ void resize_int_body(const uint8_t* __restrict__ feat, const uint8_t* __restrict__ codes, int H,
+                                                int W, int oH, int oW, const IntGeom<S>& g, float max_sigma, int channels,
+                                                int ly0, int oy0, int oy1, void* __restrict__ out, int bxi, int byi, int p,
+                                                Smem& sm) {
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  {  // hyper decode exactly like numpy in float32 (eval_lut_sr.py:623-628, resize_right2d_numpy.py:168-170)
+    const float h = __fdiv_rn((float)tid, 255.0f);
+    const float rho = __fsub_rn(__fmul_rn(h, 2.0f), 1.0f);
+    const float sig = __fmul_rn(h, max_sigma);
+    sm.tab.s2[tid] = -0.5 * kLog2e * ((double)sig * (double)sig);
+    sm.tab.sg[tid] = (double)sig;
+    sm.tab.rl[tid] = kLog2e * (double)rho;
+  }
+  __syncthreads();
+  const int lx0 = bxi * kCX - 1;    // first cell column of the block (cells start at -1)
+  const int lyb = ly0 + byi * kCY;  // first cell row of the block
+  const long long plane_sz = (long long)H * W;
+  const uint8_t* fp = feat + (long long)p * plane_sz;
+  const uint8_t* cp = codes + (long long)p * 3 * plane_sz;
+  for (int i = tid; i < (kCY + 1) * (kCX + 1); i += kCX * kCY) {
+    const int r = i / (kCX + 1), c = i - r * (kCX + 1);
+    const int sy = lyb + r, sx = lx0 + c;
+    const int cy = min(max(sy, 0), H - 1), cx = min(max(sx, 0), W - 1);  // hypers: 'edge' (:172-174)
+    const long long off = (long long)cy * W + cx;
+    const int kr = __ldcg(cp + off), kx = __ldcg(cp + plane_sz + off), ky = __ldcg(cp + 2 * plane_sz + off);
+    sm.sA[r][c] = sm.tab.s2[kx];
+    sm.sC[r][c] = sm.tab.s2[ky];
+    sm.sB[r][c] = sm.tab.rl[kr] * sm.tab.sg[kx] * sm.tab.sg[ky];
+    sm.sV[r][c] = (sy == cy && sx == cx) ? (float)__ldcg(fp + off) : 0.0f;  // image: 'constant' 0 (:208)
+  }
+  __syncthreads();
+  const int lx = lx0 + tx, ly = lyb + ty;
+  if (lx > W - 1 || ly > H - 1) return;
+  // taps t = a*2+b: row ly+b, column lx+a (same patch order as the reference, :95-98)
+  double ca[4], cb[4], cc[4];
+  float dv[4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      ca[a * 2 + b] = sm.sA[ty + b][tx + a];
+      cb[a * 2 + b] = sm.sB[ty + b][tx + a];
+      cc[a * 2 + b] = sm.sC[ty + b][tx + a];
+      dv[a * 2 + b] = sm.sV[ty + b][tx + a];
+    }
+  const float v0 = dv[0];
+  dv[1] -= v0; dv[2] -= v0; dv[3] -= v0;  // exact: integers in [-255, 255]
+  const int oyb = S * ly + g.ph_y, oxb = S * lx + g.ph_x;
+  const long long pbase = (long long)p * oH;
+  const long long hbase = (long long)(p / channels) * oH;
+  const int pc_ = p % channels;
+  constexpr bool kHoist = HOIST && S <= 4;  // S = 8 would need 64 registers for the column terms
+  double colq[kHoist ? 4 : 1][kHoist ? S : 1];
+  if (kHoist) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+      for (int mc = 0; mc < S; ++mc) colq[t][mc] = fma(cc[t], g.xc[mc][t >> 1], g.magic);
+  }
+#pragma unroll
+  for (int mr = 0; mr < S; ++mr) {
+    const int oy = oyb + mr;
+    if (oy < oy0 || oy >= oy1) continue;
+    double rowa[4], rowb[4];
+    if (kHoist) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        rowa[t] = ca[t] * g.xr[mr][t & 1];
+        rowb[t] = cb[t] * g.dr[mr][t & 1];
+      }
+    }
+    float res[S];
+#pragma unroll
+    for (int mc = 0; mc < S; ++mc) {
+      int q[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int a = t >> 1, b = t & 1;
+        if (kHoist) {
+          const double e = fma(rowb[t], g.dc[mc][a], rowa[t]);
+          q[t] = __double2loint(e + colq[t][mc]);  // round(log2 w * 2^FB), two's complement
+        } else {
+          double e = cc[t] * g.xc[mc][a];
+          e = fma(cb[t], g.pp[mr][mc][b][a], e);
+          e = fma(ca[t], g.xr[mr][b], e);
+          q[t] = __double2loint(e + g.magic);
+        }
+      }
+      res[mc] = combine_q(q, dv, v0, g.inv_scale);
+    }
+    const long long rowp = (pbase + oy) * oW, rowh = (hbase + oy) * oW;
+    const bool full = oxb >= 0 && oxb + S <= oW;
+    if (FMT == LERF_OUT_F32 && full && (S % 2 == 0)) {
+      float* o = (float*)out + rowp + oxb;
+      if (S == 8) {  // ph = 4: 16-byte aligned
+        __stcg(reinterpret_cast<float4*>(o), make_float4(res[0], res[1], res[2], res[3]));
+        __stcg(reinterpret_cast<float4*>(o + 4), make_float4(res[4 % S], res[5 % S], res[6 % S], res[7 % S]));
+      } else if (S == 4) {  // ph = 2: 8-byte aligned
+        __stcg(reinterpret_cast<float2*>(o), make_float2(res[0], res[1]));
+        __stcg(reinterpret_cast<float2*>(o + 2), make_float2(res[2 % S], res[3 % S]));
+      } else {
+        __stcg(o, res[0]);
+        __stcg(o + 1, res[1 % S]);
+      }
+    } else {
+#pragma unroll
+      for (int mc = 0; mc < S; ++mc) {
+        const int ox = oxb + mc;
+        if (ox >= 0 && ox < oW) store1<FMT>(out, rowp + ox, (rowh + ox) * channels + pc_, res[mc]);
+      }
+    }
+  }
+}
+
+// Host: geometry constants of a periodic plan.
+template <int S>
+inline IntGeom<S> make_geom(const lerf_sr_plan_impl* P, float max_sigma) {
+  IntGeom<S> g;
+  double dmax_y = 0.0, dmax_x = 0.0;
+  for (int m = 0; m < S; ++m)
+    for (int k = 0; k < 2; ++k) {
+      const double dy = P->ph_dist_y[m][k], dx = P->ph_dist_x[m][k];
+      g.dr[m][k] = dy;
+      g.dc[m][k] = dx;
+      g.xr[m][k] = dy * dy;
+      g.xc[m][k] = dx * dx;
+      dmax_y = fabs(dy) > dmax_y ? fabs(dy) : dmax_y;
+      dmax_x = fabs(dx) > dmax_x ? fabs(dx) : dmax_x;
+    }
+  for (int mr = 0; mr < S; ++mr)
+    for (int mc = 0; mc < S; ++mc)
+      for (int b = 0; b < 2; ++b)
+        for (int a = 0; a < 2; ++a) g.pp[mr][mc][b][a] = P->ph_dist_y[mr][b] * P->ph_dist_x[mc][a];
+  // fixed point: |log2 w| <= L/2 (sigma |dr| + sigma |dc|)^2 (|rho| <= 1) must stay below 2^(31-FB)
+  const double reach = (double)max_sigma * (dmax_y + dmax_x);
+  const double bound = 0.5 * kLog2e * reach * reach + 2.0;
+  int fb = 24;
+  while (fb > 8 && bound * (double)(1u << fb) >= 2147483000.0) --fb;
+  g.magic = 1.5 * (double)(1ull << (52 - fb));
+  g.inv_scale = 1.0f / (float)(1u << fb);
+  g.ph_y = P->ph_y;
+  g.ph_x = P->ph_x;
+  return g;
+}
+
+}  // namespace rsi
+}  // namespace lerf

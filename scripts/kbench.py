@@ -38,8 +38,7 @@ def timeit(fn):
 for kind in os.environ.get("KB_KINDS", "natural,uniform").split(","):
     frames = (bench.natural_frames_gpu if kind == "natural" else bench.uniform_frames_gpu)(B, 3000, dev)
     ref_feat = None
-    s1_variants = ((0, "cell (production)"), (1, "row-major minb3"), (22, "cell minb2"), (23, "cell minb3"),
-                   (25, "cell minb5"), (26, "cell minb6"), (11, "row-major EXP same-addr"), (12, "row-major EXP no loads"))
+    s1_variants = ((0, "cell (production)"), (1, "row-major minb3"), (25, "cell minb5"), (26, "cell minb6"))
     for v, name in (s1_variants[:1] if ONLY == "prod" else s1_variants):
         L.lerf_debug_lut_variant(1, v)
         feat = lp.lut_stage1(luts, frames)
@@ -49,18 +48,42 @@ for kind in os.environ.get("KB_KINDS", "natural,uniform").split(","):
         print("%-8s stage1 %-24s %8.1f us/frame" % (kind, name, timeit(lambda: lp.lut_stage1(luts, frames, out=feat))), flush=True)
     L.lerf_debug_lut_variant(1, 0)
     codes = lp.lut_stage2(luts, ref_feat)
-    s2_variants = ((0, "cell (production)"), (1, "row-major minb4"), (22, "cell minb2"), (23, "cell minb3"), (25, "cell minb5"))
+    s2_variants = ((0, "production"), (1, "row-major minb4"), (23, "cell minb3")) + tuple((40 + k, "mix v%d" % k) for k in range(10))
     for v, name in (s2_variants[:1] if ONLY == "prod" else s2_variants):
         L.lerf_debug_lut_variant(2, v)
         c2 = lp.lut_stage2(luts, ref_feat)
         assert torch.equal(c2, codes), "stage-2 variants disagree"
         print("%-8s stage2 %-24s %8.1f us/frame" % (kind, name, timeit(lambda: lp.lut_stage2(luts, ref_feat, out=c2))), flush=True)
     L.lerf_debug_lut_variant(2, 0)
+    if ONLY != "prod":  # block-swizzle weights of the cell tables (baked in at LutSet creation)
+        for hw in ():
+            L.lerf_debug_cell_hash(*hw)
+            l2 = lp.LutSet(lp.load_lut_dict(bench.LUT_DIR), device=dev)
+            for st, v in ((1, 26), (1, 25), (2, 24), (2, 23)):
+                L.lerf_debug_lut_variant(st, v)
+                if st == 1:
+                    f2 = lp.lut_stage1(l2, frames)
+                    assert torch.equal(f2, ref_feat)
+                    t = timeit(lambda: lp.lut_stage1(l2, frames, out=f2))
+                else:
+                    c2 = lp.lut_stage2(l2, ref_feat)
+                    assert torch.equal(c2, codes)
+                    t = timeit(lambda: lp.lut_stage2(l2, ref_feat, out=c2))
+                print("%-8s stage%d cell v%d hash %-12s %8.1f us/frame" % (kind, st, v, hw, t), flush=True)
+                L.lerf_debug_lut_variant(st, 0)
+            l2.close()
+        L.lerf_debug_cell_hash(9, 5, 3)
     rs = lp.SteeringGaussianResize2d(support_sz=2, max_sigma=10)
     rs.set_shape([3, bench.H, bench.W], scale_factors=[4, 4])
     for fmt in ("f32", "u8", "u8_hwc"):
         out = rs.resize_codes(ref_feat, codes, out_format=fmt)
         print("%-8s resize %-20s %8.1f us/frame" % (kind, "int-scale " + fmt, timeit(lambda: rs.resize_codes(ref_feat, codes, out_format=fmt, out=out))), flush=True)
+    if ONLY != "prod":
+        out = rs.resize_codes(ref_feat, codes, out_format="f32")
+        for v in (0, 1, 2):
+            L.lerf_debug_resize_variant(v)
+            print("%-8s resize f32 variant %d           %8.1f us/frame" % (kind, v, timeit(lambda: rs.resize_codes(ref_feat, codes, out_format="f32", out=out))), flush=True)
+        L.lerf_debug_resize_variant(0)
     L.lerf_debug_force_generic(1)
     out = rs.resize_codes(ref_feat, codes)
     print("%-8s resize %-20s %8.1f us/frame" % (kind, "generic f32", timeit(lambda: rs.resize_codes(ref_feat, codes, out=out))), flush=True)

@@ -28,14 +28,15 @@ static int rhe_div(int num, int den) {
 }
 
 extern "C" int emul_stage_cell(int stage, const int8_t* const* tables, int oC, const uint8_t* img, int P, int H, int W,
-                               uint8_t* out) {
+                               int ha, int hb, int hc, uint8_t* out) {
+  const Hash h{(uint32_t)ha, (uint32_t)hb, (uint32_t)hc};
   const int ntab = stage == 1 ? 3 : 6;
-  const size_t stride = oC == 3 ? 64 : 16;
+  const size_t stride = oC == 3 ? 48 : 16;
   std::vector<std::vector<uint8_t>> packed(ntab);
   const int ident[4] = {0, 1, 2, 3};
   for (int i = 0; i < ntab; ++i) {
     packed[i].assign((size_t)65536 * stride, 0);
-    repack_cells(tables[i], oC, ident, packed[i].data(), stride, 0);
+    repack_cells(tables[i], oC, ident, h, packed[i].data(), stride, 0);
   }
   for (int p = 0; p < P; ++p)
     for (int y = 0; y < H; ++y)
@@ -49,7 +50,7 @@ extern "C" int emul_stage_cell(int stage, const int8_t* const* tables, int oC, c
               tap_offset(mode, r, k, dy, dx);
               xw[k] = split_px(img[((size_t)p * H + clampi(y + dy, 0, H - 1)) * W + clampi(x + dx, 0, W - 1)]);
             }
-            const Simplex s = simplex_of(xw[0], xw[1], xw[2], xw[3]);
+            const Simplex s = simplex_of(xw[0], xw[1], xw[2], xw[3], h);
             const uint8_t* tab = packed[stage == 1 ? mode : 2 * mode + (r & 1)].data() + (size_t)s.cell * stride;
             for (int ch = 0; ch < oC; ++ch) {
               uint32_t q[4];

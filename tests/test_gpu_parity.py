@@ -117,8 +117,8 @@ def test_stage_kernel_variants_are_bitwise_identical(lp, oC):
     L = lp.lib()
     try:
         ref = None
-        for v in (0, 1, 22, 23, 25):
-            L.lerf_debug_lut_variant(1, v)
+        for v in (0, 1, 22, 23, 25) + ((40, 42, 44) if oC == 3 else ()):  # 40+: table-format mix (stage 2, oC = 3)
+            L.lerf_debug_lut_variant(1, v if v < 40 else 0)
             L.lerf_debug_lut_variant(2, v)
             feat = lp.lut_stage1(ls, img)
             codes = lp.lut_stage2(ls, feat)
@@ -127,6 +127,25 @@ def test_stage_kernel_variants_are_bitwise_identical(lp, oC):
             assert torch.equal(feat, ref[0]) and torch.equal(codes, ref[1]), v
     finally:
         L.lerf_debug_lut_variant(1, 0)
+        L.lerf_debug_lut_variant(2, 0)
+
+
+def test_cell_block_swizzle_does_not_change_results(lp, orc):
+    """The swizzle of the cell-packed tables is baked in at LutSet creation; any weights give the oracle's bytes."""
+    ld = random_luts(5, oC2=3)
+    img = uniform_image(17, 40, 70)
+    rf, rc, _ = orc.lut_stages(img, ld, oC=3)
+    L = lp.lib()
+    try:
+        for hw in ((0, 0, 0), (9, 5, 3), (7, 11, 13)):
+            L.lerf_debug_cell_hash(*hw)
+            ls = lp.LutSet(ld, linear=False)
+            L.lerf_debug_lut_variant(2, 24)  # cell-packed stage 2 as well
+            feat, codes = lp.lut_stages(ls, _cuda(img), "HWC")
+            assert np.array_equal(feat.cpu().numpy(), rf) and np.array_equal(codes.cpu().numpy(), rc), hw
+            ls.close()
+    finally:
+        L.lerf_debug_cell_hash(9, 5, 3)
         L.lerf_debug_lut_variant(2, 0)
 
 
@@ -303,6 +322,44 @@ def test_sr_batch_and_row_bands_are_bitwise_identical(lp, luts):
     for y0, y1 in ((0, 1), (1, 50), (50, 51), (51, 128), (128, oH)):
         sr(_cuda(imgs), out_format="f32", rows=(y0, y1), out=banded)
     assert torch.equal(banded, full)
+
+
+@pytest.mark.parametrize("fmt", ["f32", "u8_hwc"])
+def test_pipeline_kernel_equals_three_launches(lp, luts, fmt):
+    """The role-interleaved pipeline kernel (pipeline.cu, off by default) runs the same device bodies: bitwise equal,
+    for whole batches and for row bands, for every group size."""
+    _, ls = luts["g"]
+    imgs = _cuda(np.stack([uniform_image(300 + i, 45, 83) for i in range(4)]))
+    sr = lp.LerfSR(ls, 4)
+    L = lp.lib()
+    try:
+        L.lerf_debug_pipeline(0, 4, 0)
+        ref = sr(imgs, out_format=fmt).clone()
+        for minb, grp in ((4, 0), (3, 1), (2, 5), (4, 12)):
+            L.lerf_debug_pipeline(1, minb, grp)
+            assert torch.equal(sr(imgs, out_format=fmt), ref), (minb, grp)
+            band = torch.zeros_like(ref)
+            oH = sr.out_sz[0]
+            for r0, r1 in ((0, 37), (37, 100), (100, oH)):
+                sr(imgs, out_format=fmt, rows=(r0, r1), out=band)
+            assert torch.equal(band, ref), (minb, grp, "bands")
+    finally:
+        L.lerf_debug_pipeline(0, 4, 0)
+
+
+def test_resize_kernel_variants_within_tolerance(lp, orc, luts):
+    ld, ls = luts["g"]
+    img = uniform_image(61, 50, 47)
+    ref, _, _ = orc.lerf_sr(img, ld, 4, 4, linear=False)
+    sr = lp.LerfSR(ls, 4)
+    L = lp.lib()
+    try:
+        for v in (0, 1, 2):
+            L.lerf_debug_resize_variant(v)
+            out = sr(_cuda(img), out_format="f32").cpu().numpy().astype(np.float64)
+            assert _maxabs(out, ref) <= 1e-4, v  # north_star tolerance for fp32 output
+    finally:
+        L.lerf_debug_resize_variant(0)
 
 
 def test_warp_vs_oracle_random_homographies(lp, orc, luts):
