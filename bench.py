@@ -319,7 +319,10 @@ def main():
     tfile = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from the committed ncu --set full capture
     if os.path.exists(tfile):
         try:
-            roofline["traffic"] = json.load(open(tfile)).get(top)
+            t = json.load(open(tfile)).get(top)
+            roofline["traffic"] = t.get("dram_bytes_per_launch") if isinstance(t, dict) else t
+            roofline["traffic_note"] = ("DRAM bytes of one %s launch at this launch size, ncu --set full (profiles/traffic.json); "
+                                        "algorithmic bytes per launch: %d" % (top, kbytes[top]))
         except Exception:
             pass
 
