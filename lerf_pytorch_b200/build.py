@@ -22,7 +22,7 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(HERE, "csrc", s) for s in SOURCES + ["common.cuh", "lut_cell.cuh", "lut_rm.cuh", "lut_cell_body.cuh", "lut_mix.cuh", "resample_int.cuh"]] + [os.path.join(ROOT, "include", "lerf_b200.h")]
+    deps = [os.path.join(HERE, "csrc", s) for s in SOURCES + ["common.cuh", "lut_cell.cuh", "lut_rm.cuh", "lut_cell_body.cuh", "lut_mix.cuh", "lut_mt.cuh", "resample_int.cuh"]] + [os.path.join(ROOT, "include", "lerf_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

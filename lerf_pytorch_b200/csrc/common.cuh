@@ -61,6 +61,9 @@ struct lerf_luts_impl {
   int cell_hash[3];  // block swizzle weights (lut_cell.cuh), fixed when the set is created
   const uint8_t* c1[3];
   const uint8_t* c2[6];
+  // max-tap block copies of the oC = 3 stage-2 tables (lut_mt.cuh): 65536 cells x 4 blocks x 32 B each
+  void* mt_block;
+  const uint8_t* mt2[6];
 };
 
 struct lerf_sr_plan_impl {
@@ -83,6 +86,9 @@ int launch_stage_cell(const lerf_luts_impl* L, int stage, const uint8_t* in, con
 
 int launch_stage2_mix(const lerf_luts_impl* L, const uint8_t* feat, int planes, int H, int W, int y0, int y1, uint8_t* out,
                       int variant, cudaStream_t st);
+
+int launch_stage2_mt(const lerf_luts_impl* L, const uint8_t* feat, int planes, int H, int W, int y0, int y1, uint8_t* out,
+                     int variant, cudaStream_t st);
 
 // pipeline.cu
 int sr_pipeline(const lerf_luts_impl* L, int kind, const lerf_sr_plan_impl* P, const uint8_t* in, int planes, const InAddr& ia,

@@ -151,6 +151,7 @@ int lerf_luts_create(const int8_t* const host_tables[9], int oC2, int device, le
   for (int i = 0; i < 3; ++i) L->cell_hash[i] = g_cell_hash[i];
   int rc = build_cell_tables(L, host_tables);
   if (rc) {
+    cudaFree(L->mt_block);
     cudaFree(L->cell_block);
     cudaFree(L->block);
     delete L;
@@ -170,6 +171,7 @@ void lerf_luts_destroy(lerf_luts_t* luts) {
   cudaSetDevice(L->device);
   cudaFree(L->block);
   cudaFree(L->cell_block);
+  cudaFree(L->mt_block);
   delete L;
 }
 
@@ -260,6 +262,9 @@ int lerf_lut_stage2(const lerf_luts_t* luts, const uint8_t* feat, int planes, in
   rm::StageTables t;
   for (int i = 0; i < 6; ++i) t.t[i] = L->s2[i];
   InAddr ia{1, (long long)H * W, 0, W, 1};
+  if ((g_lut_variant[1] >= 60 || g_lut_variant[1] == 0) && L->oC2 == 3)  // production: max-tap block tables (lut_mt.cuh)
+    return launch_stage2_mt(L, feat, planes, H, W, y0, y1, codes, g_lut_variant[1] >= 60 ? g_lut_variant[1] - 60 : 1,
+                            (cudaStream_t)stream);
   if (g_lut_variant[1] >= 40 && L->oC2 == 3)  // table-format mix (lut_mix.cuh)
     return launch_stage2_mix(L, feat, planes, H, W, y0, y1, codes, g_lut_variant[1] - 40, (cudaStream_t)stream);
   if (g_lut_variant[1] >= 20 || (g_lut_variant[1] == 0 && L->oC2 == 1))  // oC = 3 cells thrash L1/L2 (profiles/): stage 2 stays on the row-major tables by default

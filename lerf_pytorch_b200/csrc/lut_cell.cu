@@ -6,6 +6,7 @@
 
 #include "lut_cell_body.cuh"
 #include "lut_mix.cuh"
+#include "lut_mt.cuh"
 
 namespace lerf {
 
@@ -21,35 +22,71 @@ __global__ void __launch_bounds__(kTX* kTY, MINB)
   lut_stage_cell_body<STAGE, OC>(tabs, in, ia, H, W, y0, y1, out, blockIdx.x, blockIdx.y, blockIdx.z, tile);
 }
 
-template <unsigned CELLMASK, int MINB>
+template <unsigned MTMASK, int MINB>
 __global__ void __launch_bounds__(kTX* kTY, MINB)
     lut_stage2_mix_kernel(mix::MixTables t, const uint8_t* __restrict__ feat, int H, int W, int y0, int y1,
                           uint8_t* __restrict__ out) {
   __shared__ __align__(16) unsigned char smem[mix::kSmemBytes];
-  mix::lut_stage2_mix_body<CELLMASK>(t, feat, H, W, y0, y1, out, blockIdx.x, blockIdx.y, blockIdx.z, smem);
+  mix::lut_stage2_mix_body<MTMASK>(t, feat, H, W, y0, y1, out, blockIdx.x, blockIdx.y, blockIdx.z, smem);
+}
+
+template <int NJ, int MINB, int LD>
+__global__ void __launch_bounds__(256, MINB)
+    lut_stage2_mt_kernel(mt::MtTables t, const uint8_t* __restrict__ feat, int H, int W, int y0, int y1,
+                         uint8_t* __restrict__ out) {
+  __shared__ uint2 tile[(8 * NJ + 2 * mt::kHalo) * mt::kPitch];
+  mt::lut_stage2_mt_body<NJ, LD>(t, feat, H, W, y0, y1, out, blockIdx.x, blockIdx.y, blockIdx.z, tile);
 }
 
 }  // namespace
 
-// Stage 2, oC = 3, table-format mix (lut_mix.cuh).  variant selects the pass subset that uses the cell tables.
+// Stage 2, oC = 3, max-tap block tables (lut_mt.cuh).  variant: tile height / register budget.
+int launch_stage2_mt(const lerf_luts_impl* L, const uint8_t* feat, int planes, int H, int W, int y0, int y1, uint8_t* out,
+                     int variant, cudaStream_t st) {
+  if (!L->mt2[0]) return fail(LERF_EUNSUPPORTED, "max-tap block tables were not built for this LUT set");
+  mt::MtTables t;
+  for (int i = 0; i < 6; ++i) t.t[i] = L->mt2[i];
+#define LERF_GO(NJ, B, LD)                                                                  \
+  {                                                                                         \
+    dim3 grid((W + mt::kTX - 1) / mt::kTX, (y1 - y0 + 8 * NJ - 1) / (8 * NJ), planes);      \
+    lut_stage2_mt_kernel<NJ, B, LD><<<grid, 256, 0, st>>>(t, feat, H, W, y0, y1, out);      \
+  }
+  switch (variant) {
+    case 0: LERF_GO(1, 4, 0) break;
+    case 1: LERF_GO(1, 4, 1) break;
+    case 2: LERF_GO(1, 4, 2) break;
+    case 3: LERF_GO(1, 4, 3) break;
+    case 4: LERF_GO(1, 5, 1) break;
+    case 5: LERF_GO(1, 3, 1) break;
+    case 6: LERF_GO(2, 4, 1) break;
+    case 7: LERF_GO(4, 3, 1) break;
+    case 8: LERF_GO(4, 3, 0) break;
+    default: return fail(LERF_EINVAL, "unknown stage-2 max-tap variant %d", variant);
+  }
+#undef LERF_GO
+  LERF_LAUNCHED();
+  return LERF_OK;
+}
+
+// Stage 2, oC = 3, table-format mix (lut_mix.cuh).  variant selects the pass subset that uses the max-tap blocks.
 int launch_stage2_mix(const lerf_luts_impl* L, const uint8_t* feat, int planes, int H, int W, int y0, int y1, uint8_t* out,
                       int variant, cudaStream_t st) {
+  if (!L->mt2[0]) return fail(LERF_EUNSUPPORTED, "max-tap block tables were not built for this LUT set");
   mix::MixTables t;
-  for (int i = 0; i < 6; ++i) { t.r[i] = L->s2[i]; t.c[i] = L->c2[i]; }
-  t.h = cell::Hash{(uint32_t)L->cell_hash[0], (uint32_t)L->cell_hash[1], (uint32_t)L->cell_hash[2]};
+  for (int i = 0; i < 6; ++i) { t.r[i] = L->s2[i]; t.m[i] = L->mt2[i]; }
   dim3 block(kTX * kTY), grid((W + kTX - 1) / kTX, (y1 - y0 + kTY - 1) / kTY, planes);
 #define LERF_GO(MASK, B) lut_stage2_mix_kernel<MASK, B><<<grid, block, 0, st>>>(t, feat, H, W, y0, y1, out)
-  switch (variant) {
-    case 0: LERF_GO(0x00Fu, 4); break;   // mode s, all rotations        (cell tables s r0, s r1)
-    case 1: LERF_GO(0x055u, 4); break;   // s, c rotations 0 and 2       (cell tables s r0, c r0)
-    case 2: LERF_GO(0x555u, 4); break;   // rotations 0 and 2 of s, c, t (cell tables s r0, c r0, t r0)
-    case 3: LERF_GO(0x03Fu, 4); break;
-    case 4: LERF_GO(0x0FFu, 4); break;
-    case 5: LERF_GO(0x005u, 4); break;
-    case 6: LERF_GO(0x015u, 4); break;
-    case 7: LERF_GO(0x555u, 3); break;
-    case 8: LERF_GO(0x055u, 3); break;
-    case 9: LERF_GO(0x055u, 5); break;
+  switch (variant) {  // mask bit = mode * 4 + rotation; rotations 0,2 share table r0, rotations 1,3 share table r1
+    case 0: LERF_GO(0x00Fu, 4); break;   // mode s                      (4 passes on max-tap blocks)
+    case 1: LERF_GO(0x05Fu, 4); break;   // s + c rotations 0,2         (6)
+    case 2: LERF_GO(0x0FFu, 4); break;   // s + c                       (8)
+    case 3: LERF_GO(0x5FFu, 4); break;   // s + c + t rotations 0,2     (10)
+    case 4: LERF_GO(0x005u, 4); break;   // s rotations 0,2             (2)
+    case 5: LERF_GO(0x05Fu, 3); break;
+    case 6: LERF_GO(0x0FFu, 3); break;
+    case 7: LERF_GO(0x05Fu, 5); break;
+    case 8: LERF_GO(0x0FFu, 5); break;
+    case 9: LERF_GO(0xFF0u, 4); break;   // c + t                       (8)
     default: return fail(LERF_EINVAL, "unknown stage-2 mix variant %d", variant);
   }
 #undef LERF_GO
@@ -74,6 +111,17 @@ int build_cell_tables(lerf_luts_impl* L, const int8_t* const host_tables[9]) {
   e = cudaMemcpy(L->cell_block, host.data(), total, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return fail(LERF_ECUDA, "cell-packed LUT upload failed: %s", cudaGetErrorString(e));
   L->cell_block_bytes = total;
+  if (oC == 3) {  // max-tap block tables for stage 2 (lut_mt.cuh)
+    std::vector<uint8_t> mtab(mt::kTableBytes);
+    e = cudaMalloc(&L->mt_block, 6 * mt::kTableBytes);
+    if (e != cudaSuccess) return fail(LERF_ENOMEM, "cudaMalloc for the max-tap LUT block failed: %s", cudaGetErrorString(e));
+    for (int i = 0; i < 6; ++i) {
+      mt::repack_maxtap(host_tables[3 + i], mtab.data());
+      e = cudaMemcpy((uint8_t*)L->mt_block + i * mt::kTableBytes, mtab.data(), mt::kTableBytes, cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) return fail(LERF_ECUDA, "max-tap LUT upload failed: %s", cudaGetErrorString(e));
+      L->mt2[i] = (const uint8_t*)L->mt_block + i * mt::kTableBytes;
+    }
+  }
   for (int i = 0; i < 3; ++i) L->c1[i] = (const uint8_t*)L->cell_block + i * s1_bytes;
   for (int i = 0; i < 6; ++i) L->c2[i] = (const uint8_t*)L->cell_block + 3 * s1_bytes + i * s2_bytes;
   return LERF_OK;

@@ -3,7 +3,7 @@
 // The three steps of the path -- stage 1 (reference: resample/eval_lut_sr.py:541-577), stage 2 (:579-628) and the
 // steerable resampling + epilogue (resize_right/resize_right2d_numpy.py:162-223, eval_lut_sr.py:663-665) -- are
 // each bound by a DIFFERENT unit of the SM (ncu, profiles/): stage 1 by the L1 data stage (128-bit cell gathers),
-// stage 2 by the L1 tag stage (scattered 32-bit gathers), the resampler by issue slots (FP64/XU/FP32 arithmetic).
+// stage 2 by L2 bandwidth (one 32-byte max-tap block per lookup, L1 bypassed), the resampler by issue slots (FP64/XU/FP32 arithmetic).
 // Run back to back, each leaves the other two units idle.  This kernel runs all three AT ONCE on different plane
 // groups of a batch: launch j does stage 1 of group j, stage 2 of group j-1 and the resampling of group j-2
 // (a software pipeline over the batch; stream order provides the dependencies).  Inside a launch the blocks of
@@ -11,9 +11,9 @@
 // the whole launch and all roles finish together.
 //
 // Every block is exactly one role and runs the same device body as the stand-alone kernels (lut_cell_body.cuh,
-// lut_rm.cuh, resample_int.cuh): the bytes produced are identical to the three-launch path.
+// lut_mt.cuh, resample_int.cuh): the bytes produced are identical to the three-launch path.
 #include "lut_cell_body.cuh"
-#include "lut_rm.cuh"
+#include "lut_mt.cuh"
 #include "resample_int.cuh"
 
 namespace lerf {
@@ -34,8 +34,8 @@ struct Role1 {  // stage 1 on cell-packed tables
   RoleGrid g;
 };
 
-struct Role2 {  // stage 2 (oC = 3) on row-major tables
-  rm::StageTables tabs;
+struct Role2 {  // stage 2 (oC = 3) on max-tap block tables
+  mt::MtTables tabs;
   const uint8_t* feat;
   int y0, y1;
   uint8_t* codes;
@@ -72,7 +72,7 @@ __device__ __forceinline__ void split_block(unsigned l, const RoleGrid& g, int& 
 template <int S, int FMT, int MINB>
 __global__ void __launch_bounds__(256, MINB) sr_pipeline_kernel(const __grid_constant__ PipeArgs<S> a) {
   __shared__ __align__(16) unsigned char smem_raw[sizeof(rsi::Smem)];
-  static_assert(sizeof(rsi::Smem) >= cellk::kTileWords * 4 && sizeof(rsi::Smem) >= rm::kTileBytes, "smem union");
+  static_assert(sizeof(rsi::Smem) >= cellk::kTileWords * 4 && sizeof(rsi::Smem) >= (8 + 2 * mt::kHalo) * mt::kPitch * 8, "smem union");
   // Proportional interleave: among blocks [0, b) there are floor(b * n3 / N) role-3 blocks; the others are split
   // between roles 1 and 2 the same way.  Blocks are dispatched in index order, so all roles progress at the same
   // fraction and drain together.
@@ -97,8 +97,8 @@ __global__ void __launch_bounds__(256, MINB) sr_pipeline_kernel(const __grid_con
                                      reinterpret_cast<uint32_t*>(smem_raw));
   } else {
     split_block(k - c1, a.r2.g, bx, by, p);
-    const InAddr ia{1, (long long)a.H * a.W, 0, a.W, 1};
-    rm::lut_stage_body<2, 3, 0>(a.r2.tabs, a.r2.feat, ia, a.H, a.W, a.r2.y0, a.r2.y1, a.r2.codes, bx, by, p, smem_raw);
+    mt::lut_stage2_mt_body<1, 1>(a.r2.tabs, a.r2.feat, a.H, a.W, a.r2.y0, a.r2.y1, a.r2.codes, bx, by, p,
+                                 reinterpret_cast<uint2*>(smem_raw));
   }
 }
 
@@ -125,12 +125,12 @@ int run_pipeline(const lerf_luts_impl* L, const lerf_sr_plan_impl* P, const uint
   for (int i = 0; i < 6; ++i) a.r1.tabs.t[i] = i < 3 ? L->c1[i] : nullptr;
   a.r1.tabs.h = cell::Hash{(uint32_t)L->cell_hash[0], (uint32_t)L->cell_hash[1], (uint32_t)L->cell_hash[2]};
   a.r1.in = in; a.r1.ia = ia; a.r1.y0 = f0; a.r1.y1 = f1 + 1; a.r1.feat = feat;
-  for (int i = 0; i < 6; ++i) a.r2.tabs.t[i] = L->s2[i];
+  for (int i = 0; i < 6; ++i) a.r2.tabs.t[i] = L->mt2[i];
   a.r2.feat = feat; a.r2.y0 = c0; a.r2.y1 = c1 + 1; a.r2.codes = codes;
   a.r3.feat = feat; a.r3.codes = codes; a.r3.geom = rsi::make_geom<S>(P, max_sigma); a.r3.max_sigma = max_sigma;
   a.r3.channels = ia.channels; a.r3.ly0 = ly0; a.r3.oy0 = oy0; a.r3.oy1 = oy1; a.r3.out = out;
   const int gx12 = (W + cellk::kTX - 1) / cellk::kTX;
-  static_assert(cellk::kTX == rm::kTX && cellk::kTY == rm::kTY, "stage tiles");
+  static_assert(cellk::kTX == mt::kTX && cellk::kTY == 8, "stage tiles");
   for (int j = 0; j < G + 2; ++j) {
     auto group = [&](int g, RoleGrid& rg, int gx, int gy) {
       if (g < 0 || g >= G) { rg = RoleGrid{1, 1, 0, 0}; return 0u; }
@@ -139,7 +139,7 @@ int run_pipeline(const lerf_luts_impl* L, const lerf_sr_plan_impl* P, const uint
       return (unsigned)rg.blocks();
     };
     a.n1 = group(j, a.r1.g, gx12, (f1 + 1 - f0 + cellk::kTY - 1) / cellk::kTY);
-    a.n2 = group(j - 1, a.r2.g, gx12, (c1 + 1 - c0 + rm::kTY - 1) / rm::kTY);
+    a.n2 = group(j - 1, a.r2.g, gx12, (c1 + 1 - c0 + 7) / 8);
     a.n3 = group(j - 2, a.r3.g, (W + 1 + rsi::kCX - 1) / rsi::kCX, (ly1 - ly0 + 1 + rsi::kCY - 1) / rsi::kCY);
     const unsigned long long N = (unsigned long long)a.n1 + a.n2 + a.n3;
     if (N == 0) continue;
@@ -167,7 +167,7 @@ int run_pipeline(const lerf_luts_impl* L, const lerf_sr_plan_impl* P, const uint
 // Called by lerf_sr_fused.  Returns -1 when the pipeline does not apply (the caller then issues the three plain launches).
 int sr_pipeline(const lerf_luts_impl* L, int kind, const lerf_sr_plan_impl* P, const uint8_t* in, int planes, const InAddr& ia,
                 float max_sigma, int oy0, int oy1, uint8_t* feat, uint8_t* codes, void* out, int fmt, cudaStream_t st) {
-  if (!g_pipe_enabled || kind != LERF_KIND_GAUSS || L->oC2 != 3 || !P->int_scale || planes < 2) return -1;
+  if (!g_pipe_enabled || kind != LERF_KIND_GAUSS || L->oC2 != 3 || !L->mt2[0] || !P->int_scale || planes < 2) return -1;
   if (!(max_sigma >= 0.0f) || max_sigma > 64.0f) return -1;
   if (fmt == LERF_OUT_F32 && ((uintptr_t)out & 15)) return -1;
   switch (P->int_scale) {

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../lerf_pytorch_b200/csrc/lut_cell.cuh"
+#include "../../lerf_pytorch_b200/csrc/lut_mt.cuh"
 
 using namespace lerf::cell;
 
@@ -67,6 +68,39 @@ extern "C" int emul_stage_cell(int stage, const int8_t* const* tables, int oC, c
             v = t <= 0 ? 0 : (rhe_div(t, 192) > 255 ? 255 : rhe_div(t, 192));
           }
           out[(((size_t)p * oC + ch) * H + y) * W + x] = (uint8_t)v;
+        }
+      }
+  return 0;
+}
+
+// Stage 2 (oC = 3) on max-tap blocks (lut_mt.cuh), walked like lut_stage2_mt_kernel does.
+extern "C" int emul_stage2_maxtap(const int8_t* const* tables, const uint8_t* img, int P, int H, int W, uint8_t* out) {
+  std::vector<std::vector<uint8_t>> packed(6);
+  for (int i = 0; i < 6; ++i) {
+    packed[i].assign(lerf::mt::kTableBytes, 0);
+    lerf::mt::repack_maxtap(tables[i], packed[i].data());
+  }
+  for (int p = 0; p < P; ++p)
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) {
+        int n[3] = {0, 0, 0};
+        for (int mode = 0; mode < 3; ++mode)
+          for (int r = 0; r < 4; ++r) {
+            uint32_t k[4], m[4];
+            for (int t = 0; t < 4; ++t) {
+              int dy, dx;
+              tap_offset(mode, r, t, dy, dx);
+              lerf::mt::split_px2(img[((size_t)p * H + clampi(y + dy, 0, H - 1)) * W + clampi(x + dx, 0, W - 1)], k[t], m[t]);
+            }
+            const lerf::mt::Lookup L = lerf::mt::prepare(k[0], m[0], k[1], m[1], k[2], m[2], k[3], m[3]);
+            uint32_t q[8];
+            memcpy(q, packed[2 * mode + (r & 1)].data() + (size_t)L.block * lerf::mt::kBlockBytes, 32);
+            lerf::mt::blend3(q, L, n[0], n[1], n[2]);
+          }
+        for (int ch = 0; ch < 3; ++ch) {
+          const int t = n[ch] + 127 * 192;
+          const int v = t <= 0 ? 0 : (rhe_div(t, 192) > 255 ? 255 : rhe_div(t, 192));
+          out[(((size_t)p * 3 + ch) * H + y) * W + x] = (uint8_t)v;
         }
       }
   return 0;

@@ -14,11 +14,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "cell_emul.cpp")
 LIB = os.path.join(HERE, "csrc", "libcell_emul.so")
 HDR = os.path.join(os.path.dirname(HERE), "lerf_pytorch_b200", "csrc", "lut_cell.cuh")
+HDR2 = os.path.join(os.path.dirname(HERE), "lerf_pytorch_b200", "csrc", "lut_mt.cuh")
 
 
 @pytest.fixture(scope="module")
 def emul():
-    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(HDR), os.path.getmtime(HDR2)):
         gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         env = dict(os.environ)
         env.pop("CC", None)
@@ -57,3 +58,24 @@ def test_cell_lookup_equals_oracle(emul, oC, kind):
     for hw in ((9, 5, 3), (0, 0, 0), (7, 11, 13)):
         assert np.array_equal(_run(emul, 1, t1, 1, chw, hw), feat), hw
         assert np.array_equal(_run(emul, 2, t2, oC, feat, hw), codes), hw
+
+
+@pytest.mark.parametrize("kind", ["shipped", "random"])
+def test_maxtap_block_lookup_equals_oracle(emul, kind):
+    """Stage 2 on the max-tap block format (lut_mt.cuh): one 32-byte block per lookup."""
+    luts = orc.load_luts(util.lut_dir("lerf-g"), linear=False) if kind == "shipped" else util.random_luts(31, oC2=3)
+    rng = np.random.default_rng(9)
+    img = rng.integers(0, 256, size=(33, 27, 3)).astype(np.uint8)
+    img[:6, :6] = 255
+    img[6:10, :8] = (np.arange(8) * 16)[None, :, None]  # all-lsb-zero ties
+    img[10:14, :8] = 7                                   # all-equal lsbs
+    feat, codes, _ = orc.lut_stages(img, luts, oC=3)
+    t2 = []
+    for m in "sct":
+        t2 += [luts["s2_%sr0" % m], luts["s2_%sr1" % m]]
+    tabs = [np.ascontiguousarray(t, dtype=np.int8) for t in t2]
+    arr = (ctypes.c_void_p * 6)(*[t.ctypes.data for t in tabs])
+    out = np.empty_like(codes)
+    f = np.ascontiguousarray(feat)
+    assert emul.emul_stage2_maxtap(arr, ctypes.c_void_p(f.ctypes.data), 3, f.shape[1], f.shape[2], ctypes.c_void_p(out.ctypes.data)) == 0
+    assert np.array_equal(out, codes)
