@@ -77,6 +77,9 @@ struct lerf_sr_plan_impl {
   int int_scale;   // S if out = S*in on both axes with the periodic phase pattern, else 0
   int ph_y, ph_x;  // periodic geometry: the outputs whose first tap is l are S*l + ph + m, m = 0..S-1
   double ph_dist_y[8][2], ph_dist_x[8][2];  // their distances to tap 0 / tap 1
+  void* coef_dev;    // rsi::CoefTabs for coef_sigma (resample_int.cu), allocated on first use
+  void* coef_host;
+  float coef_sigma;
 };
 
 // lut_cell.cu

@@ -30,12 +30,12 @@ __global__ void __launch_bounds__(kTX* kTY, MINB)
   mix::lut_stage2_mix_body<MTMASK>(t, feat, H, W, y0, y1, out, blockIdx.x, blockIdx.y, blockIdx.z, smem);
 }
 
-template <int NJ, int MINB, int LD>
+template <int NJ, int MINB, int LD, unsigned TABMASK = 0x3Fu>
 __global__ void __launch_bounds__(256, MINB)
     lut_stage2_mt_kernel(mt::MtTables t, const uint8_t* __restrict__ feat, int H, int W, int y0, int y1,
                          uint8_t* __restrict__ out) {
   __shared__ uint2 tile[(8 * NJ + 2 * mt::kHalo) * mt::kPitch];
-  mt::lut_stage2_mt_body<NJ, LD>(t, feat, H, W, y0, y1, out, blockIdx.x, blockIdx.y, blockIdx.z, tile);
+  mt::lut_stage2_mt_body<NJ, LD, TABMASK>(t, feat, H, W, y0, y1, out, blockIdx.x, blockIdx.y, blockIdx.z, tile);
 }
 
 }  // namespace

@@ -160,7 +160,7 @@ __device__ __forceinline__ int rhe_div192(int num) {  // round_half_even(num / 1
 }
 
 // tile: (8*NJ + 6) * kPitch uint2 of shared memory.  (bxi, byi, p) = tile column, tile row, plane.  256 threads.
-template <int NJ, int LD>
+template <int NJ, int LD, unsigned TABMASK = 0x3Fu>
 __device__ __forceinline__ void lut_stage2_mt_body(const MtTables& t, const uint8_t* __restrict__ feat, int H, int W, int y0,
                                                    int y1, uint8_t* __restrict__ out, int bxi, int byi, int p, uint2* tile) {
   constexpr int TY = 8 * NJ;
@@ -184,6 +184,7 @@ __device__ __forceinline__ void lut_stage2_mt_body(const MtTables& t, const uint
   for (int j = 0; j < NJ; ++j) acc[j][0] = acc[j][1] = acc[j][2] = 0;
   const uint2* c0 = tile + (ty + kHalo) * kPitch + tx + kHalo;
 #define LERF_TAB(M, PAR)                                                          \
+  if ((TABMASK >> (2 * M + PAR)) & 1u)                                            \
   _Pragma("unroll") for (int j = 0; j < NJ; ++j) {                                \
     if (by + ty + 8 * j < y1) {                                                   \
       const uint2* c = c0 + 8 * j * kPitch;                                       \

@@ -375,8 +375,9 @@ void lerf_sr_plan_destroy(lerf_sr_plan_t* plan) {
   if (!plan) return;
   lerf_sr_plan_impl* P = reinterpret_cast<lerf_sr_plan_impl*>(plan);
   cudaSetDevice(P->device);
-  cudaFree(P->left_y); cudaFree(P->dist_y); cudaFree(P->left_x); cudaFree(P->dist_x);
+  cudaFree(P->left_y); cudaFree(P->dist_y); cudaFree(P->left_x); cudaFree(P->dist_x); cudaFree(P->coef_dev);
   free(P->h_left_y);
+  free(P->coef_host);
   delete P;
 }
 

@@ -7,27 +7,46 @@ namespace lerf {
 
 using namespace rsi;
 
+// Device copy of the per-code tables for `max_sigma`, cached in the plan (a plan, like the reference's resizer objects,
+// is not thread-safe).  The upload is stream-ordered before the kernels that read it.
+const CoefTabs* rsi::plan_coef_tabs(const lerf_sr_plan_impl* P, float max_sigma, cudaStream_t st) {
+  lerf_sr_plan_impl* M = const_cast<lerf_sr_plan_impl*>(P);
+  if (!M->coef_dev) {
+    if (cudaMalloc(&M->coef_dev, sizeof(CoefTabs)) != cudaSuccess) return nullptr;
+    M->coef_host = malloc(sizeof(CoefTabs));
+    M->coef_sigma = -1.0f;
+  }
+  if (M->coef_sigma != max_sigma) {
+    make_coef_tabs(max_sigma, *(CoefTabs*)M->coef_host);
+    if (cudaMemcpyAsync(M->coef_dev, M->coef_host, sizeof(CoefTabs), cudaMemcpyHostToDevice, st) != cudaSuccess) return nullptr;
+    M->coef_sigma = max_sigma;
+  }
+  return (const CoefTabs*)M->coef_dev;
+}
+
 int g_variant = 0;  // testing hook: 0 = plain form, 5 blocks/SM; 1 = hoisted form, 3 blocks/SM; 2 = plain form, 4 blocks/SM
 
 template <int S, int FMT, bool HOIST, int MINB>
 __global__ void __launch_bounds__(kCX* kCY, MINB)
     resize_sr_int_gauss_kernel(const uint8_t* __restrict__ feat, const uint8_t* __restrict__ codes, int H, int W, int oH,
-                               int oW, const __grid_constant__ IntGeom<S> g, float max_sigma, int channels, int ly0,
-                               int oy0, int oy1, void* __restrict__ out) {
+                               int oW, const __grid_constant__ IntGeom<S> g, const CoefTabs* __restrict__ ct,
+                               int channels, int ly0, int oy0, int oy1, void* __restrict__ out) {
   __shared__ Smem sm;
-  resize_int_body<S, FMT, HOIST>(feat, codes, H, W, oH, oW, g, max_sigma, channels, ly0, oy0, oy1, out, blockIdx.x,
-                                 blockIdx.y, blockIdx.z, sm);
+  resize_int_body<S, FMT, HOIST>(feat, codes, H, W, oH, oW, g, ct, channels, ly0, oy0, oy1, out, blockIdx.x, blockIdx.y,
+                                 blockIdx.z, sm);
 }
 
 template <int S>
 static int launch_int(const lerf_sr_plan_impl* P, const uint8_t* feat, const uint8_t* codes, int planes, int channels,
                       float max_sigma, int oy0, int oy1, void* out, int fmt, cudaStream_t st) {
   const IntGeom<S> g = make_geom<S>(P, max_sigma);
+  const CoefTabs* ct = plan_coef_tabs(P, max_sigma, st);
+  if (!ct) return fail(LERF_ECUDA, "uploading the hyper decode tables failed");
   // cell rows touched by the output band
   const int ly0 = P->h_left_y[oy0], ly1 = P->h_left_y[oy1 - 1];
   dim3 block(kCX * kCY), grid((P->W + 1 + kCX - 1) / kCX, (ly1 - ly0 + 1 + kCY - 1) / kCY, planes);
 #define LERF_GK(F, HO, B)                                                                                              \
-  resize_sr_int_gauss_kernel<S, F, HO, B><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, max_sigma, \
+  resize_sr_int_gauss_kernel<S, F, HO, B><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, \
                                                                   channels, ly0, oy0, oy1, out)
 #define LERF_GO(F)                                   \
   if (g_variant == 1) LERF_GK(F, true, 3);           \

@@ -36,13 +36,15 @@ struct IntGeom {
   int ph_y, ph_x;         // first output of cell l is S*l + ph
 };
 
-constexpr int kCX = 32, kCY = 8;  // cells per block
-
-struct CoefTabs {           // per-code float64 tables, exact promotions of the reference's float32 values
-  double s2[256];           // -L/2 * sigma^2
-  double sg[256];           // sigma
-  double rl[256];           // L * rho
+// Per-code float64 tables, exact promotions of the reference's float32 hyper values; built once per launch on the
+// host (IEEE float32 arithmetic, same operation order as numpy) per max_sigma and kept in device memory by the plan.
+struct CoefTabs {
+  double s2[256];  // -L/2 * sigma^2
+  double sg[256];  // sigma
+  double rl[256];  // L * rho
 };
+
+constexpr int kCX = 32, kCY = 8;  // cells per block
 
 struct Smem {
   CoefTabs tab;
@@ -86,18 +88,13 @@ __device__ __forceinline__ float combine_q(const int q[4], const float dv[4], fl
 // (bxi, byi, p): the block's cell-tile column, cell-tile row and plane; 256 threads.
 template <int S, int FMT, bool HOIST>
 __device__ __forceinline__ void resize_int_body(const uint8_t* __restrict__ feat, const uint8_t* __restrict__ codes, int H,
-                                                int W, int oH, int oW, const IntGeom<S>& g, float max_sigma, int channels,
+                                                int W, int oH, int oW, const IntGeom<S>& g, const CoefTabs* __restrict__ ct, int channels,
                                                 int ly0, int oy0, int oy1, void* __restrict__ out, int bxi, int byi, int p,
                                                 Smem& sm) {
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  {  // hyper decode exactly like numpy in float32 (eval_lut_sr.py:623-628, resize_right2d_numpy.py:168-170)
-    const float h = __fdiv_rn((float)tid, 255.0f);
-    const float rho = __fsub_rn(__fmul_rn(h, 2.0f), 1.0f);
-    const float sig = __fmul_rn(h, max_sigma);
-    sm.tab.s2[tid] = -0.5 * kLog2e * ((double)sig * (double)sig);
-    sm.tab.sg[tid] = (double)sig;
-    sm.tab.rl[tid] = kLog2e * (double)rho;
-  }
+  sm.tab.s2[tid] = __ldg(ct->s2 + tid);  // global (L1/L2-resident, coalesced) -> shared memory; the tile fill indexes by code
+  sm.tab.sg[tid] = __ldg(ct->sg + tid);
+  sm.tab.rl[tid] = __ldg(ct->rl + tid);
   __syncthreads();
   const int lx0 = bxi * kCX - 1;    // first cell column of the block (cells start at -1)
   const int lyb = ly0 + byi * kCY;  // first cell row of the block
@@ -133,9 +130,10 @@ __device__ __forceinline__ void resize_int_body(const uint8_t* __restrict__ feat
   const float v0 = dv[0];
   dv[1] -= v0; dv[2] -= v0; dv[3] -= v0;  // exact: integers in [-255, 255]
   const int oyb = S * ly + g.ph_y, oxb = S * lx + g.ph_x;
-  const long long pbase = (long long)p * oH;
-  const long long hbase = (long long)(p / channels) * oH;
   const int pc_ = p % channels;
+  long long rowp = ((long long)p * oH + oyb) * oW;                  // planar index of (p, oyb, 0); advanced by oW per row
+  long long rowh = ((long long)(p / channels) * oH + oyb) * oW;     // same for the interleaved layout
+  const bool full = oxb >= 0 && oxb + S <= oW;
   constexpr bool kHoist = HOIST && S <= 4;  // S = 8 would need 64 registers for the column terms
   double colq[kHoist ? 4 : 1][kHoist ? S : 1];
   if (kHoist) {
@@ -145,7 +143,7 @@ __device__ __forceinline__ void resize_int_body(const uint8_t* __restrict__ feat
       for (int mc = 0; mc < S; ++mc) colq[t][mc] = fma(cc[t], g.xc[mc][t >> 1], g.magic);
   }
 #pragma unroll
-  for (int mr = 0; mr < S; ++mr) {
+  for (int mr = 0; mr < S; ++mr, rowp += oW, rowh += oW) {
     const int oy = oyb + mr;
     if (oy < oy0 || oy >= oy1) continue;
     double rowa[4], rowb[4];
@@ -175,8 +173,6 @@ __device__ __forceinline__ void resize_int_body(const uint8_t* __restrict__ feat
       }
       res[mc] = combine_q(q, dv, v0, g.inv_scale);
     }
-    const long long rowp = (pbase + oy) * oW, rowh = (hbase + oy) * oW;
-    const bool full = oxb >= 0 && oxb + S <= oW;
     if (FMT == LERF_OUT_F32 && full && (S % 2 == 0)) {
       float* o = (float*)out + rowp + oxb;
       if (S == 8) {  // ph = 4: 16-byte aligned
@@ -200,6 +196,18 @@ __device__ __forceinline__ void resize_int_body(const uint8_t* __restrict__ feat
 }
 
 // Host: geometry constants of a periodic plan.
+inline void make_coef_tabs(float max_sigma, CoefTabs& t) {
+  for (int c = 0; c < 256; ++c) {  // hyper decode exactly like numpy in float32 (eval_lut_sr.py:623-628, resize_right2d_numpy.py:168-170)
+    volatile float h = (float)c / 255.0f;
+    volatile float h2 = h * 2.0f;
+    volatile float rho = h2 - 1.0f;
+    volatile float sig = h * max_sigma;
+    t.s2[c] = -0.5 * kLog2e * ((double)sig * (double)sig);
+    t.sg[c] = (double)sig;
+    t.rl[c] = kLog2e * (double)rho;
+  }
+}
+
 template <int S>
 inline IntGeom<S> make_geom(const lerf_sr_plan_impl* P, float max_sigma) {
   IntGeom<S> g;
@@ -229,6 +237,8 @@ inline IntGeom<S> make_geom(const lerf_sr_plan_impl* P, float max_sigma) {
   g.ph_x = P->ph_x;
   return g;
 }
+
+const CoefTabs* plan_coef_tabs(const lerf_sr_plan_impl* P, float max_sigma, cudaStream_t st);  // resample_int.cu
 
 }  // namespace rsi
 }  // namespace lerf
