@@ -16,6 +16,7 @@ from .resize_right2d import (  # noqa: F401
     SteeringGaussianResize2d, SteeringGaussianResize2dNumpy, SteeringGaussianResize2dTorch,
     SteeringGaussianWarp2d, SteeringGaussianWarp2dNumpy, SteeringGaussianWarp2dTorch, sr_axis_tables)
 
+from . import metrics  # noqa: F401
 from .sharding import band_halo_rows, band_input_rows, image_shard, row_bands  # noqa: F401
 
 __version__ = "0.1.0"

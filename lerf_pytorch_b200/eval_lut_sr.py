@@ -1,0 +1,109 @@
+#!/usr/bin/env python
+"""Drop-in for ``python resample/eval_lut_sr.py -e <expDir> [--linear]`` of the reference, on the B200 path.
+
+Same options (common/option.py), same directory layout (``<testDir>/<dataset>/HR/*.png`` and
+``LR_bicubic/rrLR_X{sh:.2f}_{sw:.2f}/*.png``), same result files and the same printed table as
+resample/eval_lut_sr.py:747-811; the per-image body (eltr._worker, :514-744) runs as three CUDA kernels through
+``LerfSR``.  The reference hard-codes ``all_datasets = ["Set5"]`` and scales 2, 3, 4 (:777-791); here they are
+``--datasets`` and ``--scales`` with those defaults.
+
+    python -m lerf_pytorch_b200.eval_lut_sr -e models/lerf-g
+    python -m lerf_pytorch_b200.eval_lut_sr -e models/lerf-l --linear
+"""
+import os
+import sys
+
+import numpy as np
+
+from . import metrics
+from .eval_common import build_parser, check_supported, list_pngs, load_lut_dict_like_reference, load_rgb
+
+
+class Evaluator(object):
+    """``eltr`` of the reference without its module globals (eval_lut_sr.py:473-512)."""
+
+    def __init__(self, opt, lut_dict):
+        import torch
+        from . import LerfSR, LutSet
+        self.opt = opt
+        self.torch = torch
+        self.device = torch.device(opt.device)
+        self.luts = LutSet(lut_dict, linear=opt.linear, device=self.device)
+        self._sr = {}
+        self._LerfSR = LerfSR
+
+    def engine(self, scale_h, scale_w):
+        key = (float(scale_h), float(scale_w))
+        if key not in self._sr:
+            self._sr[key] = self._LerfSR(self.luts, scale_h, scale_w, max_sigma=self.opt.maxSigma,
+                                         support_sz=self.opt.suppSize)
+        return self._sr[key]
+
+    def run(self, dataset, scale_h, scale_w):
+        opt = self.opt
+        files = list_pngs(os.path.join(opt.testDir, dataset, "HR"))
+        result_path = os.path.join(opt.resultRoot, opt.expDir.rstrip("/").split("/")[-1],
+                                   "X{:.2f}_{:.2f}".format(scale_h, scale_w), dataset)
+        if opt.save and not os.path.isdir(result_path):
+            os.makedirs(result_path)
+        return [self._worker(dataset, f, scale_h, scale_w, result_path) for f in files]
+
+    def _worker(self, dataset, fname, scale_h, scale_w, result_path):
+        from PIL import Image
+        opt, torch = self.opt, self.torch
+        img_lr = load_rgb(os.path.join(opt.testDir, dataset, "LR_bicubic/rrLR_X{:.2f}_{:.2f}".format(scale_h, scale_w), fname))
+        img_gt = load_rgb(os.path.join(opt.testDir, dataset, "HR", fname))
+        sr = self.engine(scale_h, scale_w)
+        with torch.cuda.device(self.device):
+            d_in = torch.from_numpy(np.ascontiguousarray(img_lr.astype(np.uint8))).to(self.device)
+            img_out = sr(d_in, out_format="u8_hwc").cpu().numpy()           # :541-665 incl. the uint8 epilogue
+            if opt.save:
+                feat, codes = sr.stages(d_in)
+                feat = feat.cpu().numpy()
+                img_hyper = codes.cpu().numpy().astype(np.float32) / float(255)  # :623-628
+        if opt.save:
+            stem = fname.split("/")[-1][:-4]
+            Image.fromarray(img_out).save(os.path.join(result_path, "{}_{}.png".format(stem, opt.lutName)))
+            Image.fromarray(np.ascontiguousarray(feat.transpose((1, 2, 0)))).save(os.path.join(result_path, "{}_lr.png".format(stem)))
+            Image.fromarray(img_gt).save(os.path.join(result_path, "{}_gt.png".format(stem)))
+            np.save(os.path.join(result_path, "{}_{}_hyper.npy".format(fname.split("_")[-1][:-4], opt.lutName)), img_hyper)
+        return metrics.psnr_y_ssim(img_gt, img_out, scale_h, scale_w)
+
+
+def format_table(all_datasets, all_scales, results):
+    """The table of eval_lut_sr.py:793-811; results[(dataset, (sh, sw))] = list of [psnr, ssim]."""
+    lines = []
+    head = ["Scale".ljust(15, " ")]
+    for sh, sw in all_scales:
+        head.append("{:.1f}x{:.1f}\t".format(sh, sw))
+    lines.append("\t".join(head))
+    for dataset in all_datasets:
+        row = [dataset.ljust(15, " ")]
+        for sc in all_scales:
+            ps = np.asarray(results[(dataset, tuple(sc))])
+            row.append("{:.2f}/{:.4f}".format(np.mean(ps[:, 0]), np.mean(ps[:, 1])))
+        lines.append("\t".join(row))
+    return lines
+
+
+def main(argv=None):
+    p = build_parser(__doc__.splitlines()[0], './data/rrBenchmark')
+    p.add_argument('--scales', type=str, default='2x2,3x3,4x4', help='comma-separated HxW scale pairs, e.g. 2x2,2x3,3.5x3.5')
+    opt = p.parse_args(argv)
+    check_supported(opt)
+    lut_dict = load_lut_dict_like_reference(opt)
+    ev = Evaluator(opt, lut_dict)
+    all_datasets = [d for d in opt.datasets.split(",") if d]
+    all_scales = [tuple(float(v) for v in s.lower().split("x")) for s in opt.scales.split(",") if s]
+    results = {}
+    for dataset in all_datasets:
+        for sh, sw in all_scales:
+            results[(dataset, (sh, sw))] = ev.run(dataset, sh, sw)
+    lines = format_table(all_datasets, all_scales, results)
+    print("\n".join(lines))
+    return lines, results
+
+
+if __name__ == "__main__":
+    main()
+    sys.exit(0)

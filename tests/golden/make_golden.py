@@ -279,10 +279,21 @@ def main():
             g["hr_woman"] = hr[n]
         print("warp", tag, "mPSNR %.3f" % float(mp), "NaN samples:", int(np.isnan(out).sum()))
     np.savez_compressed(os.path.join(HERE, "set5_path.npz"), **g)
+    copy_set5_fixtures()
     for f in sorted(os.listdir(HERE)):
         p = os.path.join(HERE, f)
         if os.path.isfile(p):
             print("%-24s %8.1f KB" % (f, os.path.getsize(p) / 1024))
+
+
+def copy_set5_fixtures():
+    """The Set5 benchmark files (image DATA, 2.4 MB) the eval-script adapters are tested on (tests/test_eval_adapters.py):
+    data/rrBenchmark/Set5 and data/WarpBenchmark/Set5, plus the HR folder the warp script expects under WarpBenchmark
+    (the reference repo does not ship it there; it is the same five HR images)."""
+    dst = os.path.join(HERE, "data")
+    for rel in ("rrBenchmark/Set5", "WarpBenchmark/Set5"):
+        shutil.copytree(os.path.join(REF, "data", rel), os.path.join(dst, rel), dirs_exist_ok=True)
+    shutil.copytree(os.path.join(REF, "data", "rrBenchmark/Set5/HR"), os.path.join(dst, "WarpBenchmark/Set5/HR"), dirs_exist_ok=True)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,39 @@
+"""GPU: the eval-script adapters reproduce the known answers the reference publishes in scripts.sh:33-47 on the
+shipped Set5 fixtures (copied as data under tests/golden/data by make_golden.py's rules)."""
+import os
+
+import pytest
+
+from util import GOLDEN, lut_dir
+
+pytestmark = pytest.mark.gpu
+DATA = os.path.join(GOLDEN, "data")
+
+# scripts.sh:33-38 (SR, PSNR-Y/SSIM at x2, x3, x4) and :42-47 (warp, mPSNR isc / osc)
+SR_PINS = {"lerf-g": ["35.71/0.9475", "32.02/0.8980", "30.15/0.8548"], "lerf-l": ["34.84/0.9432", "30.72/0.8773", "29.13/0.8270"]}
+WARP_PINS = {"lerf-g": ["33.81", "27.89"], "lerf-l": ["32.90", "27.13"]}
+
+
+@pytest.mark.parametrize("model", ["lerf-g", "lerf-l"])
+def test_eval_lut_sr_adapter_reproduces_published_table(model, tmp_path, capsys):
+    from lerf_pytorch_b200 import eval_lut_sr
+    argv = ["-e", lut_dir(model), "--testDir", os.path.join(DATA, "rrBenchmark"), "--resultRoot", str(tmp_path)]
+    if model == "lerf-l":
+        argv.append("--linear")
+    lines, _ = eval_lut_sr.main(argv)
+    assert lines[0].split("\t")[0] == "Scale".ljust(15, " ")
+    assert lines[1].split("\t") == ["Set5".ljust(15, " ")] + SR_PINS[model]
+    assert capsys.readouterr().out.strip().splitlines()[-1] == lines[1]
+    out_dir = os.path.join(str(tmp_path), model, "X4.00_4.00", "Set5")
+    names = sorted(os.listdir(out_dir))
+    assert "baby_LUTft.png" in names and "baby_lr.png" in names and "baby_gt.png" in names and "baby_LUTft_hyper.npy" in names
+
+
+@pytest.mark.parametrize("model", ["lerf-g", "lerf-l"])
+def test_eval_lut_warp_adapter_reproduces_published_table(model, tmp_path):
+    from lerf_pytorch_b200 import eval_lut_warp
+    argv = ["-e", lut_dir(model), "--testDir", os.path.join(DATA, "WarpBenchmark"), "--resultRoot", str(tmp_path), "--no-save"]
+    if model == "lerf-l":
+        argv.append("--linear")
+    lines, _ = eval_lut_warp.main(argv)
+    assert lines[1].split("\t") == ["Set5".ljust(15, " ")] + WARP_PINS[model]
