@@ -24,22 +24,25 @@ const CoefTabs* rsi::plan_coef_tabs(const lerf_sr_plan_impl* P, float max_sigma,
   return (const CoefTabs*)M->coef_dev;
 }
 
-int g_variant = 0;  // testing hook: 0 = plain form, 5 blocks/SM; 1 = hoisted form, 3 blocks/SM; 2 = plain form, 4 blocks/SM
+// testing hook: 0 = production = ROWQ form (unsigned fixed point, row term hoisted; resample_int.cuh), 4 blocks/SM;
+// 4 = ROWQ, 5 blocks/SM; 5 = plain form (4 FP64 per exponent), 5 blocks/SM (production until r1d); 2 = plain, 4 blocks/SM;
+// 1 = fully hoisted signed form, 3 blocks/SM
+int g_variant = 0;
 
-template <int S, int FMT, bool HOIST, int MINB>
+template <int S, int FMT, int MODE, int MINB>
 __global__ void __launch_bounds__(kCX* kCY, MINB)
     resize_sr_int_gauss_kernel(const uint8_t* __restrict__ feat, const uint8_t* __restrict__ codes, int H, int W, int oH,
                                int oW, const __grid_constant__ IntGeom<S> g, const CoefTabs* __restrict__ ct,
                                int channels, int ly0, int oy0, int oy1, void* __restrict__ out) {
   __shared__ Smem sm;
-  resize_int_body<S, FMT, HOIST>(feat, codes, H, W, oH, oW, g, ct, channels, ly0, oy0, oy1, out, blockIdx.x, blockIdx.y,
+  resize_int_body<S, FMT, MODE>(feat, codes, H, W, oH, oW, g, ct, channels, ly0, oy0, oy1, out, blockIdx.x, blockIdx.y,
                                  blockIdx.z, sm);
 }
 
 template <int S>
 static int launch_int(const lerf_sr_plan_impl* P, const uint8_t* feat, const uint8_t* codes, int planes, int channels,
                       float max_sigma, int oy0, int oy1, void* out, int fmt, cudaStream_t st) {
-  const IntGeom<S> g = make_geom<S>(P, max_sigma);
+  const IntGeom<S> g = make_geom<S>(P, max_sigma, /*unsigned_form=*/g_variant == 0 || g_variant == 4);
   const CoefTabs* ct = plan_coef_tabs(P, max_sigma, st);
   if (!ct) return fail(LERF_ECUDA, "uploading the hyper decode tables failed");
   // cell rows touched by the output band
@@ -49,9 +52,11 @@ static int launch_int(const lerf_sr_plan_impl* P, const uint8_t* feat, const uin
   resize_sr_int_gauss_kernel<S, F, HO, B><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, \
                                                                   channels, ly0, oy0, oy1, out)
 #define LERF_GO(F)                                   \
-  if (g_variant == 1) LERF_GK(F, true, 3);           \
-  else if (g_variant == 2) LERF_GK(F, false, 4);     \
-  else LERF_GK(F, false, 5)
+  if (g_variant == 1) LERF_GK(F, 1, 3);              \
+  else if (g_variant == 2) LERF_GK(F, 0, 4);         \
+  else if (g_variant == 5) LERF_GK(F, 0, 5);         \
+  else if (g_variant == 4) LERF_GK(F, 2, 5);         \
+  else LERF_GK(F, 2, 4)
   switch (fmt) {
     case LERF_OUT_F32: LERF_GO(LERF_OUT_F32); break;
     case LERF_OUT_U8: LERF_GO(LERF_OUT_U8); break;

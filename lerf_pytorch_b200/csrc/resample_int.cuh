@@ -83,10 +83,32 @@ __device__ __forceinline__ float combine_q(const int q[4], const float dv[4], fl
   return v0 + qn;
 }
 
+// Unsigned form (ROWQ variant): q[t] = round(-log2 w * 2^FB) + 16 >= 0 as uint32 (the form is positive semi-definite, so
+// -log2 w >= 0 and the whole 32-bit range carries magnitude: one more fraction bit than the signed form).  The tap
+// with the SMALLEST q has weight 1; neg_scale = -2^-FB.
+__device__ __forceinline__ float combine_uq(const unsigned q[4], const float dv[4], float v0, float neg_scale) {
+  const unsigned qm = min(min(q[0], q[1]), min(q[2], q[3]));
+  float w[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float x = __uint2float_rn(q[t] - qm) * neg_scale;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w[t]) : "f"(x));
+  }
+  const float den = (w[0] + w[1]) + (w[2] + w[3]);
+  const float num = fmaf(w[1], dv[1], fmaf(w[2], dv[2], w[3] * dv[3]));
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
+  float qn = num * r;
+  qn = fmaf(fmaf(-den, qn, num), r, qn);
+  return v0 + qn;
+}
+
 // Streaming traffic (codes, feat, outputs) uses .cg loads/stores: it must not evict the LUT lines that the stage
 // roles of the pipeline kernel keep in L1.
 // (bxi, byi, p): the block's cell-tile column, cell-tile row and plane; 256 threads.
-template <int S, int FMT, bool HOIST>
+// MODE: 0 = plain (4 FP64 per exponent), 1 = fully hoisted signed form, 2 = ROWQ: unsigned fixed point with the row
+// term and the rounding constant hoisted per output row (2 FP64 per exponent, 8 more registers than MODE 0).
+template <int S, int FMT, int MODE>
 __device__ __forceinline__ void resize_int_body(const uint8_t* __restrict__ feat, const uint8_t* __restrict__ codes, int H,
                                                 int W, int oH, int oW, const IntGeom<S>& g, const CoefTabs* __restrict__ ct, int channels,
                                                 int ly0, int oy0, int oy1, void* __restrict__ out, int bxi, int byi, int p,
@@ -134,7 +156,8 @@ __device__ __forceinline__ void resize_int_body(const uint8_t* __restrict__ feat
   long long rowp = ((long long)p * oH + oyb) * oW;                  // planar index of (p, oyb, 0); advanced by oW per row
   long long rowh = ((long long)(p / channels) * oH + oyb) * oW;     // same for the interleaved layout
   const bool full = oxb >= 0 && oxb + S <= oW;
-  constexpr bool kHoist = HOIST && S <= 4;  // S = 8 would need 64 registers for the column terms
+  constexpr bool kHoist = MODE == 1 && S <= 4;
+  constexpr bool kRowQ = MODE == 2;  // S = 8 would need 64 registers for the column terms
   double colq[kHoist ? 4 : 1][kHoist ? S : 1];
   if (kHoist) {
 #pragma unroll
@@ -154,6 +177,10 @@ __device__ __forceinline__ void resize_int_body(const uint8_t* __restrict__ feat
         rowb[t] = cb[t] * g.dr[mr][t & 1];
       }
     }
+    if (kRowQ) {  // geometry constants are NEGATED in this mode (make_geom): rowa = magic - a' dr^2 >= magic
+#pragma unroll
+      for (int t = 0; t < 4; ++t) rowa[t] = fma(ca[t], g.xr[mr][t & 1], g.magic);
+    }
     float res[S];
 #pragma unroll
     for (int mc = 0; mc < S; ++mc) {
@@ -161,7 +188,13 @@ __device__ __forceinline__ void resize_int_body(const uint8_t* __restrict__ feat
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const int a = t >> 1, b = t & 1;
-        if (kHoist) {
+        if (kRowQ) {
+          // order matters: the two non-negative terms first, the signed cross term last, so no partial sum drops
+          // below the binade of `magic` (which carries a +16-unit guard for the two extra roundings)
+          double e = fma(cc[t], g.xc[mc][a], rowa[t]);
+          e = fma(cb[t], g.pp[mr][mc][b][a], e);
+          q[t] = __double2loint(e);
+        } else if (kHoist) {
           const double e = fma(rowb[t], g.dc[mc][a], rowa[t]);
           q[t] = __double2loint(e + colq[t][mc]);  // round(log2 w * 2^FB), two's complement
         } else {
@@ -171,7 +204,12 @@ __device__ __forceinline__ void resize_int_body(const uint8_t* __restrict__ feat
           q[t] = __double2loint(e + g.magic);
         }
       }
-      res[mc] = combine_q(q, dv, v0, g.inv_scale);
+      if (kRowQ) {
+        const unsigned uq[4] = {(unsigned)q[0], (unsigned)q[1], (unsigned)q[2], (unsigned)q[3]};
+        res[mc] = combine_uq(uq, dv, v0, g.inv_scale);
+      } else {
+        res[mc] = combine_q(q, dv, v0, g.inv_scale);
+      }
     }
     if (FMT == LERF_OUT_F32 && full && (S % 2 == 0)) {
       float* o = (float*)out + rowp + oxb;
@@ -208,8 +246,9 @@ inline void make_coef_tabs(float max_sigma, CoefTabs& t) {
   }
 }
 
+// unsigned_form: constants for resize_int_body MODE 2 (negated geometry, magic = 2^(52-FB) + 16 units, inv_scale < 0).
 template <int S>
-inline IntGeom<S> make_geom(const lerf_sr_plan_impl* P, float max_sigma) {
+inline IntGeom<S> make_geom(const lerf_sr_plan_impl* P, float max_sigma, bool unsigned_form = false) {
   IntGeom<S> g;
   double dmax_y = 0.0, dmax_x = 0.0;
   for (int m = 0; m < S; ++m)
@@ -229,6 +268,24 @@ inline IntGeom<S> make_geom(const lerf_sr_plan_impl* P, float max_sigma) {
   // fixed point: |log2 w| <= L/2 (sigma |dr| + sigma |dc|)^2 (|rho| <= 1) must stay below 2^(31-FB)
   const double reach = (double)max_sigma * (dmax_y + dmax_x);
   const double bound = 0.5 * kLog2e * reach * reach + 2.0;
+  if (unsigned_form) {
+    int fb = 26;
+    while (fb > 8 && bound * (double)(1u << fb) >= 4294967000.0) --fb;
+    g.magic = (double)(1ull << (52 - fb)) + 16.0 / (double)(1u << fb);
+    g.inv_scale = -1.0f / (float)(1u << fb);
+    for (int m = 0; m < S; ++m)
+      for (int k = 0; k < 2; ++k) {
+        g.xr[m][k] = -g.xr[m][k];
+        g.xc[m][k] = -g.xc[m][k];
+      }
+    for (int mr = 0; mr < S; ++mr)
+      for (int mc = 0; mc < S; ++mc)
+        for (int b = 0; b < 2; ++b)
+          for (int a = 0; a < 2; ++a) g.pp[mr][mc][b][a] = -g.pp[mr][mc][b][a];
+    g.ph_y = P->ph_y;
+    g.ph_x = P->ph_x;
+    return g;
+  }
   int fb = 24;
   while (fb > 8 && bound * (double)(1u << fb) >= 2147483000.0) --fb;
   g.magic = 1.5 * (double)(1ull << (52 - fb));

@@ -18,6 +18,7 @@ from util import lut_dir, natural_image, uniform_image  # noqa: E402
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 1356
 ld = lp.load_lut_dict(lut_dir("lerf-g"))
 ls = lp.LutSet(ld)
+lp.lib().lerf_debug_resize_variant(int(os.environ.get("ACC_VARIANT", "0")))  # int-scale kernel variant under test
 for name, img in (("uniform", uniform_image(3000, rows, 2040)), ("natural", natural_image(3001, min(rows, 400), 2040))):
     for S in (4, 2):
         t = time.time()

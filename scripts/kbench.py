@@ -80,7 +80,7 @@ for kind in os.environ.get("KB_KINDS", "natural,uniform").split(","):
         print("%-8s resize %-20s %8.1f us/frame" % (kind, "int-scale " + fmt, timeit(lambda: rs.resize_codes(ref_feat, codes, out_format=fmt, out=out))), flush=True)
     if ONLY != "prod":
         out = rs.resize_codes(ref_feat, codes, out_format="f32")
-        for v in (0, 1, 2):
+        for v in (0, 1, 2, 4, 5):
             L.lerf_debug_resize_variant(v)
             print("%-8s resize f32 variant %d           %8.1f us/frame" % (kind, v, timeit(lambda: rs.resize_codes(ref_feat, codes, out_format="f32", out=out))), flush=True)
         L.lerf_debug_resize_variant(0)
