@@ -263,7 +263,7 @@ int lerf_lut_stage2(const lerf_luts_t* luts, const uint8_t* feat, int planes, in
   for (int i = 0; i < 6; ++i) t.t[i] = L->s2[i];
   InAddr ia{1, (long long)H * W, 0, W, 1};
   if ((g_lut_variant[1] >= 60 || g_lut_variant[1] == 0) && L->oC2 == 3)  // production: max-tap block tables (lut_mt.cuh)
-    return launch_stage2_mt(L, feat, planes, H, W, y0, y1, codes, g_lut_variant[1] >= 60 ? g_lut_variant[1] - 60 : 1,
+    return launch_stage2_mt(L, feat, planes, H, W, y0, y1, codes, g_lut_variant[1] >= 60 ? g_lut_variant[1] - 60 : 10,  // 10: single-word taps, 5 blocks/SM
                             (cudaStream_t)stream);
   if (g_lut_variant[1] >= 40 && L->oC2 == 3)  // table-format mix (lut_mix.cuh)
     return launch_stage2_mix(L, feat, planes, H, W, y0, y1, codes, g_lut_variant[1] - 40, (cudaStream_t)stream);

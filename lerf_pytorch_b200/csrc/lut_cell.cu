@@ -30,12 +30,12 @@ __global__ void __launch_bounds__(kTX* kTY, MINB)
   mix::lut_stage2_mix_body<MTMASK>(t, feat, H, W, y0, y1, out, blockIdx.x, blockIdx.y, blockIdx.z, smem);
 }
 
-template <int NJ, int MINB, int LD, unsigned TABMASK = 0x3Fu>
+template <int NJ, int MINB, int LD, unsigned TABMASK = 0x3Fu, typename PX = uint2>
 __global__ void __launch_bounds__(256, MINB)
     lut_stage2_mt_kernel(mt::MtTables t, const uint8_t* __restrict__ feat, int H, int W, int y0, int y1,
                          uint8_t* __restrict__ out) {
-  __shared__ uint2 tile[(8 * NJ + 2 * mt::kHalo) * mt::kPitch];
-  mt::lut_stage2_mt_body<NJ, LD, TABMASK>(t, feat, H, W, y0, y1, out, blockIdx.x, blockIdx.y, blockIdx.z, tile);
+  __shared__ PX tile[(8 * NJ + 2 * mt::kHalo) * mt::kPitch];
+  mt::lut_stage2_mt_body<NJ, LD, TABMASK, PX>(t, feat, H, W, y0, y1, out, blockIdx.x, blockIdx.y, blockIdx.z, tile);
 }
 
 }  // namespace
@@ -61,6 +61,16 @@ int launch_stage2_mt(const lerf_luts_impl* L, const uint8_t* feat, int planes, i
     case 6: LERF_GO(2, 4, 1) break;
     case 7: LERF_GO(4, 3, 1) break;
     case 8: LERF_GO(4, 3, 0) break;
+#define LERF_GO1(NJ, B, LD)                                                                                  \
+  {                                                                                                          \
+    dim3 grid((W + mt::kTX - 1) / mt::kTX, (y1 - y0 + 8 * NJ - 1) / (8 * NJ), planes);                       \
+    lut_stage2_mt_kernel<NJ, B, LD, 0x3Fu, uint32_t><<<grid, 256, 0, st>>>(t, feat, H, W, y0, y1, out);     \
+  }
+    case 9: LERF_GO1(1, 4, 1) break;   // single-word taps (prepare1)
+    case 10: LERF_GO1(1, 5, 1) break;
+    case 11: LERF_GO1(1, 6, 1) break;
+    case 12: LERF_GO1(2, 4, 1) break;
+#undef LERF_GO1
     default: return fail(LERF_EINVAL, "unknown stage-2 max-tap variant %d", variant);
   }
 #undef LERF_GO

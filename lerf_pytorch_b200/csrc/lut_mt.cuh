@@ -73,6 +73,35 @@ LERF_HD Lookup prepare(uint32_t ka, uint32_t ma, uint32_t kb, uint32_t mb, uint3
   return L;
 }
 
+// Single-word form (production since r1e): taps as cell::split_px words (lsb << 24 | msb << 8, the stage-1 tile format),
+// so a tap costs one 4-byte shared-memory word instead of a uint2.  The low byte of a sort key carries the tap id twice,
+// (4+t) << 4 | t; the msb bits 8..11 ride along in the keys and only break lsb ties (tied vertices have weight 0).
+// L.block is returned as a BYTE offset (cell * 128 + t1 * 32) in this form.
+LERF_HD Lookup prepare1(uint32_t wa, uint32_t wb, uint32_t wc, uint32_t wd) {
+  Lookup L;
+  const uint32_t acc = ((wa * 16u + wb) * 16u + wc) * 16u + wd;  // bits 8..23 = cell index (the lsb bytes land above)
+  int k1 = (int)(wa | 0x40u), k2 = (int)(wb | 0x51u), k3 = (int)(wc | 0x62u), k4 = (int)(wd | 0x73u);
+  int t;
+  t = cell::imax(k1, k2); k2 = cell::imin(k1, k2); k1 = t;
+  t = cell::imax(k3, k4); k4 = cell::imin(k3, k4); k3 = t;
+  t = cell::imax(k1, k3); k3 = cell::imin(k1, k3); k1 = t;
+  t = cell::imax(k2, k4); k4 = cell::imin(k2, k4); k2 = t;
+  t = cell::imax(k2, k3); k3 = cell::imin(k2, k3); k2 = t;
+  L.block = ((acc & 0x00FFFF00u) >> 1) + (((uint32_t)k1 & 0x30u) << 1);  // bits 4,5 of the key's low byte = t1
+  const uint32_t s24 = ((uint32_t)k2 & 0x0Fu) | ((uint32_t)k4 & ~0x0Fu);  // byte 0: nibble 0 = t2, nibble 1 = 4+t4
+  L.sel = prmt(s24, (uint32_t)k1, 0x4440u);                              // byte 1: nibbles 2,3 = t1, 4+t1
+  const uint32_t f12 = prmt((uint32_t)k1, (uint32_t)k2, 0x0073u);   // [f1, f2, x, x]
+  const uint32_t f34 = prmt((uint32_t)k3, (uint32_t)k4, 0x0073u);   // [f3, f4, x, x]
+  const uint32_t F = prmt(f12, f34, 0x5410u);                       // [f1, f2, f3, f4]
+  const uint32_t Wd = F - (F >> 8);                                 // [f1-f2, f2-f3, f3-f4, f4]
+  const uint32_t G = 0x10101010u - F;                               // [16-f1, ...]
+  L.w = prmt(Wd, G, 0x3421u);                                       // [w2, w3, w0, w4]
+  L.w1[0] = Wd & 0xFFu;
+  L.w1[1] = prmt(Wd, 0u, 0x4404u);
+  L.w1[2] = prmt(Wd, 0u, 0x4044u);
+  return L;
+}
+
 // q[0..7] = the block's 8 words.
 LERF_HD void blend3(const uint32_t q[8], const Lookup& L, int& n0, int& n1, int& n2) {
   n0 = dp4a_ss(prmt(q[0], q[1], L.sel), L.w, dp4a_ss(q[6], L.w1[0], n0));
@@ -152,6 +181,22 @@ __device__ __forceinline__ void pass(const uint8_t* __restrict__ tab, const uint
   blend3(q, L, n0, n1, n2);
 }
 
+template <int MODE, int R, int LD>
+__device__ __forceinline__ void pass(const uint8_t* __restrict__ tab, const uint32_t* c, int& n0, int& n1, int& n2) {
+  const Lookup L = prepare1(c[Tap<MODE, R, 0>::dy * kPitch + Tap<MODE, R, 0>::dx], c[Tap<MODE, R, 1>::dy * kPitch + Tap<MODE, R, 1>::dx],
+                            c[Tap<MODE, R, 2>::dy * kPitch + Tap<MODE, R, 2>::dx], c[Tap<MODE, R, 3>::dy * kPitch + Tap<MODE, R, 3>::dx]);
+  uint32_t q[8];
+  load_block<LD>(tab + L.block, q);  // byte offset in the single-word form
+  blend3(q, L, n0, n1, n2);
+}
+
+__device__ __forceinline__ void store_px(uint2* t, uint32_t v) {
+  uint2 w;
+  split_px2(v, w.x, w.y);
+  *t = w;
+}
+__device__ __forceinline__ void store_px(uint32_t* t, uint32_t v) { *t = cell::split_px(v); }
+
 __device__ __forceinline__ int rhe_div192(int num) {  // round_half_even(num / 192), num > 0
   const int t = num + 96;
   int q = t / 192;
@@ -159,10 +204,11 @@ __device__ __forceinline__ int rhe_div192(int num) {  // round_half_even(num / 1
   return q;
 }
 
-// tile: (8*NJ + 6) * kPitch uint2 of shared memory.  (bxi, byi, p) = tile column, tile row, plane.  256 threads.
-template <int NJ, int LD, unsigned TABMASK = 0x3Fu>
+// tile: (8*NJ + 6) * kPitch pixels of shared memory, PX = uint32_t (single-word form, production) or uint2 (r1d form).
+// (bxi, byi, p) = tile column, tile row, plane.  256 threads.
+template <int NJ, int LD, unsigned TABMASK = 0x3Fu, typename PX = uint2>
 __device__ __forceinline__ void lut_stage2_mt_body(const MtTables& t, const uint8_t* __restrict__ feat, int H, int W, int y0,
-                                                   int y1, uint8_t* __restrict__ out, int bxi, int byi, int p, uint2* tile) {
+                                                   int y1, uint8_t* __restrict__ out, int bxi, int byi, int p, PX* tile) {
   constexpr int TY = 8 * NJ;
   const int bx = bxi * kTX, by = y0 + byi * TY;
   const uint8_t* src = feat + (long long)p * H * W;
@@ -170,9 +216,7 @@ __device__ __forceinline__ void lut_stage2_mt_body(const MtTables& t, const uint
   for (int i = tid; i < (TY + 2 * kHalo) * (kTX + 2 * kHalo); i += 256) {
     const int r = i / (kTX + 2 * kHalo), c = i - r * (kTX + 2 * kHalo);
     const int gy = min(max(by + r - kHalo, 0), H - 1), gx = min(max(bx + c - kHalo, 0), W - 1);
-    uint2 v;
-    split_px2(__ldcg(src + (long long)gy * W + gx), v.x, v.y);
-    tile[r * kPitch + c] = v;
+    store_px(tile + r * kPitch + c, __ldcg(src + (long long)gy * W + gx));
   }
   __syncthreads();
   const int lane = tid & 31, wrp = tid >> 5;
@@ -182,12 +226,12 @@ __device__ __forceinline__ void lut_stage2_mt_body(const MtTables& t, const uint
   int acc[NJ][3];
 #pragma unroll
   for (int j = 0; j < NJ; ++j) acc[j][0] = acc[j][1] = acc[j][2] = 0;
-  const uint2* c0 = tile + (ty + kHalo) * kPitch + tx + kHalo;
+  const PX* c0 = tile + (ty + kHalo) * kPitch + tx + kHalo;
 #define LERF_TAB(M, PAR)                                                          \
   if ((TABMASK >> (2 * M + PAR)) & 1u)                                            \
   _Pragma("unroll") for (int j = 0; j < NJ; ++j) {                                \
     if (by + ty + 8 * j < y1) {                                                   \
-      const uint2* c = c0 + 8 * j * kPitch;                                       \
+      const PX* c = c0 + 8 * j * kPitch;                                          \
       pass<M, PAR, LD>(t.t[2 * M + PAR], c, acc[j][0], acc[j][1], acc[j][2]);         \
       pass<M, PAR + 2, LD>(t.t[2 * M + PAR], c, acc[j][0], acc[j][1], acc[j][2]);     \
     }                                                                             \

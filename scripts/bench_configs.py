@@ -67,7 +67,7 @@ def cfg1():
 
 
 def cfg2():
-    luts = lp.LutSet(lp.load_lut_dict(os.path.join(LUTS, "lerf-l")), linear=True, device=dev)
+    luts = lp.LutSet(lp.load_lut_dict(os.path.join(LUTS, "lerf-l"), linear=True), linear=True, device=dev)
     imgs = torch.cat([natural(1, 512, 512, 2000 + i) for i in range(16)])
     sr = lp.LerfSR(luts, 3.5)
     out = sr(imgs)

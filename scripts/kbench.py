@@ -48,7 +48,7 @@ for kind in os.environ.get("KB_KINDS", "natural,uniform").split(","):
         print("%-8s stage1 %-24s %8.1f us/frame" % (kind, name, timeit(lambda: lp.lut_stage1(luts, frames, out=feat))), flush=True)
     L.lerf_debug_lut_variant(1, 0)
     codes = lp.lut_stage2(luts, ref_feat)
-    s2_variants = ((0, "production (max-tap v1)"), (1, "row-major minb4"), (23, "cell-48B minb3")) + tuple((60 + k, "max-tap v%d" % k) for k in range(9)) + ((42, "mix rm+max-tap 8/12"),)
+    s2_variants = ((0, "production (max-tap v10)"), (1, "row-major minb4"), (23, "cell-48B minb3")) + tuple((60 + k, "max-tap v%d" % k) for k in range(13)) + ((42, "mix rm+max-tap 8/12"),)
     for v, name in (s2_variants[:1] if ONLY == "prod" else s2_variants):
         L.lerf_debug_lut_variant(2, v)
         c2 = lp.lut_stage2(luts, ref_feat)

@@ -22,6 +22,11 @@ METRICS = [
     ("l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum", "global load t-stage wavefronts"),
     ("l1tex__t_sector_hit_rate.pct", "L1 sector hit rate % (LUT gathers)"),
     ("lts__t_sector_hit_rate.pct", "L2 sector hit rate %"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 throughput % of peak"),
+    ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "L1/TEX throughput % of peak"),
+    ("l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed", "L1 LSU writeback stage %"),
+    ("l1tex__m_xbar2l1tex_read_bytes.sum", "L2 -> L1 read bytes"),
+    ("lts__t_sectors_srcunit_tex_op_read.sum", "L2 sectors read by L1"),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", "shared load wavefronts"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum", "shared load bank conflicts"),
     ("dram__bytes_read.sum", "DRAM read"),

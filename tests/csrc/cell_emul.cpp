@@ -105,3 +105,36 @@ extern "C" int emul_stage2_maxtap(const int8_t* const* tables, const uint8_t* im
       }
   return 0;
 }
+
+// Same stage on the single-word tap form (lut_mt.cuh prepare1, production since r1e).
+extern "C" int emul_stage2_maxtap1(const int8_t* const* tables, const uint8_t* img, int P, int H, int W, uint8_t* out) {
+  std::vector<std::vector<uint8_t>> packed(6);
+  for (int i = 0; i < 6; ++i) {
+    packed[i].assign(lerf::mt::kTableBytes, 0);
+    lerf::mt::repack_maxtap(tables[i], packed[i].data());
+  }
+  for (int p = 0; p < P; ++p)
+    for (int y = 0; y < H; ++y)
+      for (int x = 0; x < W; ++x) {
+        int n[3] = {0, 0, 0};
+        for (int mode = 0; mode < 3; ++mode)
+          for (int r = 0; r < 4; ++r) {
+            uint32_t w[4];
+            for (int t = 0; t < 4; ++t) {
+              int dy, dx;
+              tap_offset(mode, r, t, dy, dx);
+              w[t] = lerf::cell::split_px(img[((size_t)p * H + clampi(y + dy, 0, H - 1)) * W + clampi(x + dx, 0, W - 1)]);
+            }
+            const lerf::mt::Lookup L = lerf::mt::prepare1(w[0], w[1], w[2], w[3]);  // single-word form: L.block is a byte offset
+            uint32_t q[8];
+            memcpy(q, packed[2 * mode + (r & 1)].data() + (size_t)L.block, 32);
+            lerf::mt::blend3(q, L, n[0], n[1], n[2]);
+          }
+        for (int ch = 0; ch < 3; ++ch) {
+          const int t = n[ch] + 127 * 192;
+          const int v = t <= 0 ? 0 : (rhe_div(t, 192) > 255 ? 255 : rhe_div(t, 192));
+          out[(((size_t)p * 3 + ch) * H + y) * W + x] = (uint8_t)v;
+        }
+      }
+  return 0;
+}

@@ -77,5 +77,7 @@ def test_maxtap_block_lookup_equals_oracle(emul, kind):
     arr = (ctypes.c_void_p * 6)(*[t.ctypes.data for t in tabs])
     out = np.empty_like(codes)
     f = np.ascontiguousarray(feat)
-    assert emul.emul_stage2_maxtap(arr, ctypes.c_void_p(f.ctypes.data), 3, f.shape[1], f.shape[2], ctypes.c_void_p(out.ctypes.data)) == 0
-    assert np.array_equal(out, codes)
+    for fn in (emul.emul_stage2_maxtap, emul.emul_stage2_maxtap1):  # uint2 taps (r1d) and single-word taps (r1e)
+        out[:] = 0
+        assert fn(arr, ctypes.c_void_p(f.ctypes.data), 3, f.shape[1], f.shape[2], ctypes.c_void_p(out.ctypes.data)) == 0
+        assert np.array_equal(out, codes)

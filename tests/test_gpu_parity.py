@@ -117,7 +117,7 @@ def test_stage_kernel_variants_are_bitwise_identical(lp, oC):
     L = lp.lib()
     try:
         ref = None
-        for v in (0, 1, 22, 23, 25) + ((40, 42, 44, 60, 61, 62, 63, 67) if oC == 3 else ()):  # 40+: table-format mix (stage 2, oC = 3)
+        for v in (0, 1, 22, 23, 25) + ((40, 42, 44, 60, 61, 62, 63, 67, 69, 70, 72) if oC == 3 else ()):  # 40+: table-format mix (stage 2, oC = 3)
             L.lerf_debug_lut_variant(1, v if v < 40 else 0)
             L.lerf_debug_lut_variant(2, v)
             feat = lp.lut_stage1(ls, img)
