@@ -184,13 +184,20 @@ class ClockSampler(object):
 # ---------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port on the host cores
 # ---------------------------------------------------------------------------------------------------
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_port_rate(rows, seed, repeats=1, threads=None):
     """Time the oracle C port (stage 1 + stage 2 + set_shape/resize + uint8 epilogue) on a `rows` x 2040 band of a
     cfg-3 frame.  Returns (out MPix/s, seconds per run, threads)."""
     from oracle import lerf_oracle as orc
     orc.build()
-    if threads:
-        orc.set_threads(threads)
+    # all the host threads this process may use -- torchrun exports OMP_NUM_THREADS=1, which would make this a 1-core run
+    orc.set_threads(threads or host_threads())
     nthreads = orc.max_threads()
     luts = orc.load_luts(LUT_DIR, linear=False)
     img = natural_frame_numpy(seed, rows, W)

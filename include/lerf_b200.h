@@ -129,7 +129,9 @@ int lerf_resize_sr(int kind, const lerf_sr_plan_t* plan, const uint8_t* feat, co
                    int planes, int channels, float max_sigma, int oy0, int oy1, void* out,
                    int out_format, lerf_stream_t stream);
 
-/* Testing hook: when on, integer scales also take the generic-scale kernel (the two must agree). */
+/* Testing hook.  0 = production dispatch (cell-owner kernel for integer scales, tile kernel for other scales >= 1,
+ * fast warp kernel); 1 = only the float64 operation-order kernels (the parity path); 2 = like 0 without the cell-owner
+ * kernel, so integer scales take the tile kernel too.  All must agree within the fp32 tolerance. */
 void lerf_debug_force_generic(int on);
 
 /* Testing / tuning hook for the integer-scale kernel: 0 = production form; 1 = hoisted-FP64 form (80 registers);

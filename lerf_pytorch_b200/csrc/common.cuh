@@ -77,6 +77,7 @@ struct lerf_sr_plan_impl {
   int int_scale;   // S if out = S*in on both axes with the periodic phase pattern, else 0
   int ph_y, ph_x;  // periodic geometry: the outputs whose first tap is l are S*l + ph + m, m = 0..S-1
   double ph_dist_y[8][2], ph_dist_x[8][2];  // their distances to tap 0 / tap 1
+  int tile_ok;     // every 32 x 32 output group has its taps in a 33 x 33 input window (any scale >= 1), |dist| <= 1: resample_tile.cu
   void* coef_dev;    // rsi::CoefTabs for coef_sigma (resample_int.cu), allocated on first use
   void* coef_host;
   float coef_sigma;
@@ -103,5 +104,12 @@ int resize_sr_int_gauss(const lerf_sr_plan_impl* P, const uint8_t* feat, const u
                         float max_sigma, int oy0, int oy1, void* out, int fmt, cudaStream_t st);
 
 void resize_int_config(int variant);
+
+// resample_tile.cu: fast paths for uint8 code inputs; return -1 when they do not apply
+int resize_sr_tile(int kind, const lerf_sr_plan_impl* P, const uint8_t* feat, const uint8_t* codes, int planes, int channels,
+                   float max_sigma, int oy0, int oy1, void* out, int fmt, cudaStream_t st);
+int warp_fast(int kind, const uint8_t* feat, const uint8_t* codes, int planes, int channels, int H, int W, int oH, int oW,
+              const double minv[9], int pad0_y, int pad0_x, int mpad0_y, int mpad0_x, int border, float max_sigma, void* out,
+              int fmt, uint8_t* mask, cudaStream_t st);
 
 }  // namespace lerf

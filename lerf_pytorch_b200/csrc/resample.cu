@@ -330,7 +330,7 @@ static int fill_geom(WarpGeom& g, int H, int W, int oH, int oW, const double min
 
 using namespace lerf;
 
-static bool g_force_generic = false;
+static int g_force_generic = 0;  // 0 = production; 1 = float64 parity kernels only; 2 = no cell-owner kernel (tile kernel for integer scales too)
 
 extern "C" {
 
@@ -367,6 +367,14 @@ int lerf_sr_plan_create(int H, int W, int oH, int oW, const int32_t* left_y, con
   const int sy = detect_int_scale(H, oH, left_y, dist_y, P->ph_y, P->ph_dist_y);
   const int sx = detect_int_scale(W, oW, left_x, dist_x, P->ph_x, P->ph_dist_x);
   P->int_scale = (sy && sy == sx) ? sy : 0;
+  P->tile_ok = 1;  // resample_tile.cu: a block's 32 x 32 outputs must find their taps in a 33 x 33 input window,
+                   // and the fixed-point exponent assumes |distance| <= 1 (+ eps)
+  for (int o = 0; o < oH && P->tile_ok; ++o)
+    if (left_y[o + 31 < oH ? o + 31 : oH - 1] - left_y[o] > 31 || fabs(dist_y[2 * o]) > 1.0000005 || fabs(dist_y[2 * o + 1]) > 1.0000005)
+      P->tile_ok = 0;
+  for (int o = 0; o < oW && P->tile_ok; ++o)
+    if (left_x[o + 31 < oW ? o + 31 : oW - 1] - left_x[o] > 31 || fabs(dist_x[2 * o]) > 1.0000005 || fabs(dist_x[2 * o + 1]) > 1.0000005)
+      P->tile_ok = 0;
   *out = reinterpret_cast<lerf_sr_plan_t*>(P);
   return LERF_OK;
 }
@@ -399,17 +407,23 @@ int lerf_resize_sr(int kind, const lerf_sr_plan_t* plan, const uint8_t* feat, co
   if (planes == 0 || oy0 == oy1) return LERF_OK;
   CodeSrc hyp{codes};
   if (kind == LERF_KIND_GAUSS) {
-    if (P->int_scale && !g_force_generic) {  // periodic geometry: cell-owner kernel (resample_int.cu)
+    if (P->int_scale && g_force_generic == 0) {  // periodic geometry: cell-owner kernel (resample_int.cu)
       rc = resize_sr_int_gauss(P, feat, codes, planes, channels, max_sigma, oy0, oy1, out, out_format, (cudaStream_t)stream);
       if (rc != -1) return rc;
     }
+  }
+  if (g_force_generic != 1) {  // any scale >= 1: tile kernel (resample_tile.cu); the float64 kernels below are the parity path
+    rc = resize_sr_tile(kind, P, feat, codes, planes, channels, max_sigma, oy0, oy1, out, out_format, (cudaStream_t)stream);
+    if (rc != -1) return rc;
+  }
+  if (kind == LERF_KIND_GAUSS) {
     return launch_sr<LERF_KIND_GAUSS>(P, feat, hyp, planes, channels, max_sigma, oy0, oy1, out, out_format, (cudaStream_t)stream);
   }
   return launch_sr<LERF_KIND_LINEAR>(P, feat, hyp, planes, channels, max_sigma, oy0, oy1, out, out_format, (cudaStream_t)stream);
 }
 
 /* Testing hook: route integer scales through the generic kernel too (parity tests compare both). */
-void lerf_debug_force_generic(int on) { g_force_generic = on != 0; }
+void lerf_debug_force_generic(int on) { g_force_generic = on; }
 
 /* Testing / tuning hook for the integer-scale kernel (see lerf_b200.h). */
 void lerf_debug_resize_variant(int variant) { resize_int_config(variant); }
@@ -439,6 +453,11 @@ int lerf_warp(int kind, const uint8_t* feat, const uint8_t* codes, int planes, i
   int rc = fill_geom(g, H, W, oH, oW, minv, pad0_y, pad0_x, mask_pad0_y, mask_pad0_x, mask_border);
   if (rc) return rc;
   if (oH == 0 || oW == 0) return LERF_OK;
+  if (g_force_generic != 1) {  // fast path (resample_tile.cu); the float64 kernel below is the parity path
+    rc = warp_fast(kind, feat, codes, planes, channels, H, W, oH, oW, minv, pad0_y, pad0_x, mask_pad0_y, mask_pad0_x,
+                   mask_border, max_sigma, out, out_format, mask, (cudaStream_t)stream);
+    if (rc != -1) return rc;
+  }
   CodeSrc hyp{codes};
   if (kind == LERF_KIND_GAUSS)
     return launch_warp<LERF_KIND_GAUSS>(feat, hyp, g, planes, channels, max_sigma, out, out_format, mask, (cudaStream_t)stream);

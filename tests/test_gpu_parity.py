@@ -438,6 +438,65 @@ def test_int_scale_kernel_vs_generic_kernel_and_oracle(lp, orc, luts, S):
     assert float(np.max(np.abs(outs[0]["f32"].astype(np.float64) - outs[1]["f32"]))) <= 1e-4
 
 
+@pytest.mark.parametrize("model,sh,sw", [("g", 3.5, 3.5), ("g", 1.3, 2.6), ("l", 3.5, 3.5), ("l", 1.0, 2.25), ("g", 4, 4), ("l", 2, 2)])
+def test_tile_kernel_vs_float64_kernel_and_oracle(lp, orc, luts, model, sh, sw):
+    """Any scale >= 1 takes the tile kernel (resample_tile.cu); the float64 operation-order kernel (force_generic 1) is a
+    second implementation of the same operator.  Level 2 routes integer scales through the tile kernel as well."""
+    ld, ls = luts[model]
+    img = uniform_image(77, 83, 121)
+    sr = lp.LerfSR(ls, sh, sw)
+    dimg = _cuda(img)
+    ref, _, _ = orc.lerf_sr(img, ld, sh, sw, linear=(model == "l"))
+    outs = {}
+    try:
+        for level in (2, 1):
+            lp.lib().lerf_debug_force_generic(level)
+            outs[level] = {f: sr(dimg, out_format=f).cpu().numpy() for f in ("f32", "u8", "u8_hwc")}
+            if level == 2:  # output row bands (blocks start at the band's first row) reproduce the full run bit for bit
+                full = torch.from_numpy(outs[2]["f32"]).cuda()
+                band = torch.zeros_like(full)
+                oH = full.shape[-2]
+                for r0, r1 in ((0, oH // 3), (oH // 3, 2 * oH // 3 + 1), (2 * oH // 3 + 1, oH)):
+                    sr(dimg, out_format="f32", rows=(r0, r1), out=band.unsqueeze(0))
+                assert torch.equal(band, full)
+    finally:
+        lp.lib().lerf_debug_force_generic(0)
+    for level in (2, 1):
+        err = _maxabs(outs[level]["f32"], ref)
+        print("%s x%sx%s %s kernel: max-abs err %.3g" % (model, sh, sw, "tile" if level == 2 else "float64", err))
+        assert err <= FP32_TOL
+        want = orc.to_uint8_hwc(ref)
+        assert np.max(np.abs(outs[level]["u8_hwc"].astype(int) - want.astype(int))) <= 1
+        assert np.array_equal(np.transpose(outs[level]["u8"], (1, 2, 0)), outs[level]["u8_hwc"])
+
+
+def test_fast_warp_kernel_vs_float64_kernel(lp, orc, luts):
+    """lerf_warp takes the fast kernel (resample_tile.cu); force_generic 1 is the float64 operation-order kernel.  Both must
+    match the oracle inside the validity mask and give the same mask."""
+    img = uniform_image(4100, 72, 64)
+    M = np.array([[3.1, 0.35, 20.0], [-0.2, 2.7, 30.0], [2e-4, -3e-4, 1.0]])
+    for model in ("g", "l"):
+        ld, ls = luts[model]
+        wp = lp.LerfWarp(ls)
+        ref, rmask, _, _ = orc.lerf_warp(img, ld, M, (3, 260, 250), linear=(model == "l"))
+        inside = np.broadcast_to(rmask[0], ref.shape)
+        assert inside.sum() > 1000
+        try:
+            for level in (0, 1):
+                lp.lib().lerf_debug_force_generic(level)
+                out, mask = wp(_cuda(img), M, (260, 250), out_format="f32")
+                assert np.array_equal(mask.cpu().numpy().astype(bool), rmask[0])
+                err = float(np.max(np.abs(out.cpu().numpy().astype(np.float64)[inside] - ref[inside])))
+                print("warp %s %s kernel: max-abs err inside mask %.3g" % (model, "fast" if level == 0 else "float64", err))
+                assert err <= FP32_TOL
+                u8, _ = wp(_cuda(img), M, (260, 250), out_format="u8_hwc")
+                want = orc.to_uint8_hwc(np.where(inside, ref, 0.0))
+                got = u8.cpu().numpy() * rmask[0][:, :, None]
+                assert np.max(np.abs(got.astype(int) - want.astype(int))) <= 1
+        finally:
+            lp.lib().lerf_debug_force_generic(0)
+
+
 def test_extreme_hypers_no_nan(lp):
     """All-taps-underflow hazard: sigma = max everywhere, rho = +-1, far taps -> weights ~ 2^-288."""
     H, W = 12, 14
