@@ -134,6 +134,11 @@ int lerf_resize_sr(int kind, const lerf_sr_plan_t* plan, const uint8_t* feat, co
  * kernel, so integer scales take the tile kernel too.  All must agree within the fp32 tolerance. */
 void lerf_debug_force_generic(int on);
 
+/* Testing hook for lerf_warp's fast Gaussian kernel: 1 (default) = every input sample is first decoded into a 32-byte
+ * record (stream-ordered scratch from cudaMallocAsync) and a tap is one 256-bit gather; 0 = taps are gathered from
+ * feat/codes and decoded through tables.  Same arithmetic, identical results. */
+void lerf_debug_warp_records(int on);
+
 /* Testing / tuning hook for the integer-scale kernel: 0 = production form; 1 = hoisted-FP64 form (80 registers);
  * 2 = production form at a 64-register budget.  All forms stay within the 1e-4 bar. */
 void lerf_debug_resize_variant(int variant);

@@ -29,6 +29,7 @@ PROTOTYPES = {
     "lerf_sr_plan_destroy": (None, [_c_p]),
     "lerf_resize_sr": (_c_i, [_c_i, _c_p, _c_p, _c_p, _c_i, _c_i, _c_f, _c_i, _c_i, _c_p, _c_i, _c_p]),
     "lerf_debug_force_generic": (None, [_c_i]),
+    "lerf_debug_warp_records": (None, [_c_i]),
     "lerf_debug_resize_variant": (None, [_c_i]),
     "lerf_debug_lut_variant": (None, [_c_i, _c_i]),
     "lerf_debug_cell_hash": (None, [_c_i, _c_i, _c_i]),

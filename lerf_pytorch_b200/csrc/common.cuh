@@ -111,5 +111,6 @@ int resize_sr_tile(int kind, const lerf_sr_plan_impl* P, const uint8_t* feat, co
 int warp_fast(int kind, const uint8_t* feat, const uint8_t* codes, int planes, int channels, int H, int W, int oH, int oW,
               const double minv[9], int pad0_y, int pad0_x, int mpad0_y, int mpad0_x, int border, float max_sigma, void* out,
               int fmt, uint8_t* mask, cudaStream_t st);
+void warp_fast_config(int use_records);
 
 }  // namespace lerf

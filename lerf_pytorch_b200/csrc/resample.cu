@@ -425,6 +425,9 @@ int lerf_resize_sr(int kind, const lerf_sr_plan_t* plan, const uint8_t* feat, co
 /* Testing hook: route integer scales through the generic kernel too (parity tests compare both). */
 void lerf_debug_force_generic(int on) { g_force_generic = on; }
 
+/* Testing hook: 0 = the fast warp kernel reads img/codes + tables, 1 (default) = per-sample records (resample_tile.cu). */
+void lerf_debug_warp_records(int on) { warp_fast_config(on); }
+
 /* Testing / tuning hook for the integer-scale kernel (see lerf_b200.h). */
 void lerf_debug_resize_variant(int variant) { resize_int_config(variant); }
 

@@ -178,6 +178,41 @@ __global__ void __launch_bounds__(kOX* kTY)
 // ---------------------------------------------------------------------------------------------------------------
 // warp: one thread = one output pixel, all planes; float64 geometry in the reference's operation order
 // ---------------------------------------------------------------------------------------------------------------
+// One 32-byte record per input sample for the Gaussian warp: the tap's three exponent coefficients and its value, so
+// the warp kernel fetches a tap with ONE 256-bit gather instead of four byte gathers, three table reads and two DMULs.
+struct __align__(32) TapRec {
+  double a, b, c;  // -L/2 sx^2, L rho sx sy, -L/2 sy^2   (L = log2 e)
+  float v, pad;
+};
+
+__global__ void __launch_bounds__(256)
+    warp_records_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ codes, long long plane_sz, float max_sigma,
+                        TapRec* __restrict__ rec) {
+  __shared__ double t_s2[256], t_sg[256], t_rl[256];
+  {
+    const int c = threadIdx.x;  // float32 decode exactly like numpy (eval_lut_warp.py:186-191, resize_right2d_numpy.py:522-524)
+    const float h = __fdiv_rn((float)c, 255.0f);
+    const float rho = __fsub_rn(__fmul_rn(h, 2.0f), 1.0f);
+    const float sig = __fmul_rn(h, max_sigma);
+    t_s2[c] = __dmul_rn(-0.5 * kLog2e, __dmul_rn((double)sig, (double)sig));
+    t_sg[c] = (double)sig;
+    t_rl[c] = __dmul_rn(kLog2e, (double)rho);
+  }
+  __syncthreads();
+  const int p = blockIdx.y;
+  const uint8_t* cp = codes + (long long)p * 3 * plane_sz;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < plane_sz; i += (long long)gridDim.x * 256) {
+    const int kr = __ldcg(cp + i), kx = __ldcg(cp + plane_sz + i), ky = __ldcg(cp + 2 * plane_sz + i);
+    TapRec r;
+    r.a = t_s2[kx];
+    r.c = t_s2[ky];
+    r.b = t_rl[kr] * t_sg[kx] * t_sg[ky];
+    r.v = (float)__ldcg(img + (long long)p * plane_sz + i);
+    r.pad = 0.0f;
+    rec[(long long)p * plane_sz + i] = r;
+  }
+}
+
 struct WarpGeomF {
   double m[9];
   int H, W, oH, oW;
@@ -189,12 +224,14 @@ __constant__ double kEps32f = 1.1920928955078125e-07;
 
 __device__ __forceinline__ int clampi3(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
-template <int KIND, int FMT, bool CLAMP>
+// REC: Gaussian taps come from the TapRec array (`rec`) instead of img/codes + tables.
+template <int KIND, int FMT, bool CLAMP, bool REC>
 __global__ void __launch_bounds__(256)
-    warp_fast_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ codes, const WarpGeomF g, int planes,
-                     int channels, float max_sigma, const FixQ fq, void* __restrict__ out, uint8_t* __restrict__ mask) {
-  __shared__ double t_s2[256], t_sg[256], t_rl[256];  // Gauss: -L/2 sigma^2, sigma, L rho;  linear: t_s2 = alpha
-  {
+    warp_fast_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ codes, const TapRec* __restrict__ rec,
+                     const WarpGeomF g, int planes, int channels, float max_sigma, const FixQ fq, void* __restrict__ out,
+                     uint8_t* __restrict__ mask) {
+  __shared__ double t_s2[REC ? 1 : 256], t_sg[REC ? 1 : 256], t_rl[REC ? 1 : 256];  // Gauss: -L/2 sigma^2, sigma, L rho;  linear: t_s2 = alpha
+  if (!REC) {
     const int c = threadIdx.y * 32 + threadIdx.x;  // 256 threads = 256 codes; float32 decode exactly like numpy
     const float h = __fdiv_rn((float)c, 255.0f);
     const float rho = __fsub_rn(__fmul_rn(h, 2.0f), 1.0f);
@@ -279,10 +316,6 @@ __global__ void __launch_bounds__(256)
     const uint8_t* fp = img + (long long)p * plane_sz;
     const uint8_t* cp = codes + (long long)p * (KIND == LERF_KIND_GAUSS ? 3 : 1) * plane_sz;
     float dv[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) dv[t] = inside[t] ? (float)__ldg(fp + off[t]) : 0.0f;
-    const float v0 = dv[0];
-    dv[1] -= v0; dv[2] -= v0; dv[3] -= v0;
     float res;
     if (KIND == LERF_KIND_GAUSS) {
       unsigned q[4];
@@ -292,13 +325,31 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
           const int t = a * 2 + b;
-          const int kr = __ldg(cp + off[t]), kx = __ldg(cp + plane_sz + off[t]), ky = __ldg(cp + 2 * plane_sz + off[t]);
-          double e = t_s2[kx] * ndr2[b];
-          e = fma(t_s2[ky], ndc2[a], e);
-          e = fma(t_rl[kr] * t_sg[kx] * t_sg[ky], npp[b][a], e);
+          double ca, cb, cc;
+          if (REC) {
+            uint32_t r0, r1, r2, r3, r4, r5, r6, r7;  // one 256-bit load of the tap's record
+            asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5), "=r"(r6), "=r"(r7)
+                : "l"(rec + (long long)p * plane_sz + off[t]));
+            ca = __hiloint2double((int)r1, (int)r0);
+            cb = __hiloint2double((int)r3, (int)r2);
+            cc = __hiloint2double((int)r5, (int)r4);
+            dv[t] = inside[t] ? __uint_as_float(r6) : 0.0f;
+          } else {
+            const int kr = __ldg(cp + off[t]), kx = __ldg(cp + plane_sz + off[t]), ky = __ldg(cp + 2 * plane_sz + off[t]);
+            ca = t_s2[kx];
+            cc = t_s2[ky];
+            cb = t_rl[kr] * t_sg[kx] * t_sg[ky];
+            dv[t] = inside[t] ? (float)__ldg(fp + off[t]) : 0.0f;
+          }
+          double e = ca * ndr2[b];
+          e = fma(cc, ndc2[a], e);
+          e = fma(cb, npp[b][a], e);
           ef[t] = e;  // -log2 w >= 0
           q[t] = (unsigned)__double2loint(e + fq.magic);
         }
+      const float v0 = dv[0];
+      dv[1] -= v0; dv[2] -= v0; dv[3] -= v0;
       if (!far) {
         res = combine_uq(q, dv, v0, fq.neg_scale);
       } else {
@@ -312,6 +363,10 @@ __global__ void __launch_bounds__(256)
         res = combine_lin(w, dv, v0);
       }
     } else {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) dv[t] = inside[t] ? (float)__ldg(fp + off[t]) : 0.0f;
+      const float v0 = dv[0];
+      dv[1] -= v0; dv[2] -= v0; dv[3] -= v0;
       float w[4];
 #pragma unroll
       for (int a = 0; a < 2; ++a)
@@ -361,6 +416,32 @@ int resize_sr_tile(int kind, const lerf_sr_plan_impl* P, const uint8_t* feat, co
   return LERF_OK;
 }
 
+static bool g_warp_records = true;  // testing hook (lerf_debug_warp_records): false = table form of the fast kernel
+
+// Stream-ordered scratch for the records: a library-owned memory pool per device that keeps its memory between calls
+// (the default pool hands it back to the driver at every synchronisation: 6 ms per 100 MB call, measured).
+static cudaMemPool_t scratch_pool() {
+  static cudaMemPool_t pools[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!pools[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool = nullptr;
+    if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return nullptr;
+    }
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    pools[dev] = pool;
+  }
+  return pools[dev];
+}
+
 // Called by lerf_warp for uint8 code inputs.  Returns -1 when this path does not apply.
 int warp_fast(int kind, const uint8_t* feat, const uint8_t* codes, int planes, int channels, int H, int W, int oH, int oW,
               const double minv[9], int pad0_y, int pad0_x, int mpad0_y, int mpad0_x, int border, float max_sigma, void* out,
@@ -372,22 +453,42 @@ int warp_fast(int kind, const uint8_t* feat, const uint8_t* codes, int planes, i
   g.pad0_y = pad0_y; g.pad0_x = pad0_x; g.mpad0_y = mpad0_y; g.mpad0_x = mpad0_x; g.border = border;
   const FixQ fq = make_fixq(max_sigma);
   dim3 block(32, 8), grid((oW + 31) / 32, (oH + 7) / 8, 1);
-#define LERF_GK(K, F, CL) \
-  warp_fast_kernel<K, F, CL><<<grid, block, 0, st>>>(feat, codes, g, planes, channels, max_sigma, fq, out, mask)
-#define LERF_GO(F)                                                  \
-  if (kind == LERF_KIND_GAUSS) LERF_GK(LERF_KIND_GAUSS, F, false);   \
-  else if (max_sigma > 1.0f) LERF_GK(LERF_KIND_LINEAR, F, true);    \
-  else LERF_GK(LERF_KIND_LINEAR, F, false)
+  // Gaussian: decode every input sample once into a 32-byte record (stream-ordered scratch), then gather records.
+  TapRec* rec = nullptr;
+  if (kind == LERF_KIND_GAUSS && out && planes > 0 && g_warp_records) {
+    const long long n = (long long)planes * H * W;
+    cudaMemPool_t pool = scratch_pool();
+    if (pool && cudaMallocFromPoolAsync((void**)&rec, (size_t)n * sizeof(TapRec), pool, st) == cudaSuccess) {
+      dim3 rgrid((unsigned)min((long long)((long long)H * W + 255) / 256, 4096LL), planes);
+      warp_records_kernel<<<rgrid, 256, 0, st>>>(feat, codes, (long long)H * W, max_sigma, rec);
+      LERF_LAUNCHED();
+    } else {
+      (void)cudaGetLastError();  // no scratch: the table form below needs none
+      rec = nullptr;
+    }
+  }
+#define LERF_GK(K, F, CL, RC) \
+  warp_fast_kernel<K, F, CL, RC><<<grid, block, 0, st>>>(feat, codes, rec, g, planes, channels, max_sigma, fq, out, mask)
+#define LERF_GO(F)                                                         \
+  if (kind == LERF_KIND_GAUSS && rec) LERF_GK(LERF_KIND_GAUSS, F, false, true); \
+  else if (kind == LERF_KIND_GAUSS) LERF_GK(LERF_KIND_GAUSS, F, false, false);  \
+  else if (max_sigma > 1.0f) LERF_GK(LERF_KIND_LINEAR, F, true, false);     \
+  else LERF_GK(LERF_KIND_LINEAR, F, false, false)
   switch (fmt) {
     case LERF_OUT_F32: LERF_GO(LERF_OUT_F32); break;
     case LERF_OUT_U8: LERF_GO(LERF_OUT_U8); break;
     case LERF_OUT_U8_HWC: LERF_GO(LERF_OUT_U8_HWC); break;
-    default: return fail(LERF_EINVAL, "unknown out_format %d", fmt);
+    default:
+      if (rec) cudaFreeAsync(rec, st);
+      return fail(LERF_EINVAL, "unknown out_format %d", fmt);
   }
 #undef LERF_GO
 #undef LERF_GK
+  if (rec) cudaFreeAsync(rec, st);  // stream-ordered: released after the warp kernel
   LERF_LAUNCHED();
   return LERF_OK;
 }
+
+void warp_fast_config(int use_records) { g_warp_records = use_records != 0; }
 
 }  // namespace lerf

@@ -413,6 +413,74 @@ def test_full_size_properties_cfg3(lp, luts):
     assert float((inner - inner[:, :1, :1]).abs().max()) <= 1e-4
 
 
+def test_full_size_cfg2_vs_oracle(lp, orc, luts):
+    """BASELINE.json cfg-2 at full size: LeRF-L x3.5 on a batch of 16 512x512 images in ONE batched call; parity is the
+    oracle looped per image.  The oracle needs ~1 s per image, so 4 of the 16 are checked."""
+    ld, ls = luts["l"]
+    imgs = np.stack([natural_image(2000 + i, 512, 512) for i in range(16)])
+    sr = lp.LerfSR(ls, 3.5)
+    out = sr(_cuda(imgs), out_format="f32")
+    u8 = sr(_cuda(imgs), out_format="u8_hwc")
+    assert tuple(out.shape) == (16, 3, 1792, 1792)
+    for i in (0, 5, 10, 15):
+        ref, _, _ = orc.lerf_sr(imgs[i], ld, 3.5, 3.5, linear=True)
+        err = _maxabs(out[i].cpu().numpy(), ref)
+        print("cfg-2 image %d: fp32 max-abs err %.3g" % (i, err))
+        assert err <= FP32_TOL
+        assert np.max(np.abs(u8[i].cpu().numpy().astype(int) - orc.to_uint8_hwc(ref).astype(int))) <= 1
+
+
+def test_full_size_cfg4_vs_oracle(lp, orc, luts):
+    """BASELINE.json cfg-4 at full size: one in-scale random homography (SURVEY 8d generator, seed 4000) on a 1024x1024
+    input to a 3072x3072 canvas, against the oracle inside the validity mask; the masks must be identical."""
+    ld, ls = luts["g"]
+    img = natural_image(4000, 1024, 1024)
+    rng = np.random.default_rng(4000)
+    a, d = rng.uniform(2.0, 4.0, 2)
+    b, c = rng.uniform(-0.15, 0.15, 2) * max(a, d)
+    gh = rng.uniform(-0.6, 0.6, 2) / 1024
+    M = np.array([[a, b, 0.0], [c, d, 0.0], [gh[0], gh[1], 1.0]])
+    corners = np.array([[0, 0, 1], [1024, 0, 1], [0, 1024, 1], [1024, 1024, 1]], dtype=np.float64).T
+    w = M @ corners
+    w = w[:2] / w[2]
+    M = np.array([[1, 0, 1536 - w[0].mean()], [0, 1, 1536 - w[1].mean()], [0, 0, 1.0]]) @ M
+    out, mask = lp.LerfWarp(ls)(_cuda(img), M, (3072, 3072), out_format="f32")
+    ref, rmask, _, _ = orc.lerf_warp(img, ld, M, (3, 3072, 3072))
+    assert np.array_equal(mask.cpu().numpy().astype(bool), rmask[0])
+    inside = np.broadcast_to(rmask[0], ref.shape)
+    assert inside.sum() > 3_000_000
+    err = float(np.max(np.abs(out.cpu().numpy().astype(np.float64)[inside] - ref[inside])))
+    print("cfg-4 full size: max-abs err inside mask %.3g over %d samples" % (err, int(inside.sum())))
+    assert err <= FP32_TOL
+
+
+def test_full_size_properties_cfg5_band(lp, luts):
+    """BASELINE.json cfg-5 (3840x2160 x8 -> 30720x17280, row-band sharded over 8 GPUs): what one rank computes.  (1) The
+    rank's output band computed from the whole input equals (2) the same rows computed from the input band + 7-row
+    halo only (what the rank would be sent), bit for bit; (3) a 64-row piece equals the oracle."""
+    from oracle import lerf_oracle as orc
+    ld, ls = luts["g"]
+    img = uniform_image(5000, 2160, 3840)
+    sr = lp.LerfSR(ls, 8)
+    oH, oW = sr.set_shape(2160, 3840)
+    assert (oH, oW) == (17280, 30720)
+    g, G = 3, 8
+    y0, y1 = g * oH // G, (g + 1) * oH // G          # this rank's output rows
+    band = torch.zeros((3, y1 - y0 + 0, oW), dtype=torch.float32, device="cuda")
+    full_like = torch.empty((1, 3, oH, oW), dtype=torch.float32, device="cuda")  # 6.4 GB; only the band is written
+    sr(_cuda(img), out_format="f32", rows=(y0, y1), out=full_like)
+    band.copy_(full_like[0, :, y0:y1])
+    del full_like
+    r0, r1 = y0 // 8 - 7, y1 // 8 + 7                 # input rows of the band + 7-row halo
+    crop = lp.LerfSR(ls, 8)(_cuda(img[r0:r1]), out_format="f32")
+    assert torch.equal(crop[:, 8 * 7:8 * 7 + (y1 - y0)], band)
+    ref, _, _ = orc.lerf_sr(img[r0:r0 + 22, :512], ld, 8, 8)   # rows 7..14 of this crop are exact (7-row halo)
+    got = band[:, :64, :8 * 505].cpu().numpy()
+    err = _maxabs(got, ref[:, 56:120, :8 * 505])
+    print("cfg-5 band piece: max-abs err %.3g" % err)
+    assert err <= FP32_TOL
+
+
 @pytest.mark.parametrize("S", [2, 3, 4, 8])
 def test_int_scale_kernel_vs_generic_kernel_and_oracle(lp, orc, luts, S):
     """The periodic-geometry (cell-owner) kernel and the generic kernel are two implementations of the same operator."""
@@ -482,6 +550,12 @@ def test_fast_warp_kernel_vs_float64_kernel(lp, orc, luts):
         inside = np.broadcast_to(rmask[0], ref.shape)
         assert inside.sum() > 1000
         try:
+            if model == "g":  # records form (default) and table form of the fast kernel: same arithmetic, same bits
+                o1, _ = wp(_cuda(img), M, (260, 250), out_format="f32")
+                lp.lib().lerf_debug_warp_records(0)
+                o0, _ = wp(_cuda(img), M, (260, 250), out_format="f32")
+                lp.lib().lerf_debug_warp_records(1)
+                assert torch.equal(o0, o1)
             for level in (0, 1):
                 lp.lib().lerf_debug_force_generic(level)
                 out, mask = wp(_cuda(img), M, (260, 250), out_format="f32")
@@ -495,6 +569,7 @@ def test_fast_warp_kernel_vs_float64_kernel(lp, orc, luts):
                 assert np.max(np.abs(got.astype(int) - want.astype(int))) <= 1
         finally:
             lp.lib().lerf_debug_force_generic(0)
+            lp.lib().lerf_debug_warp_records(1)
 
 
 def test_extreme_hypers_no_nan(lp):
