@@ -49,6 +49,13 @@ extern "C" {
 #define LERF_OUT_U8 1      /* uint8 planar, clip(round_half_even(x),0,255) (eval_lut_sr.py:663) */
 #define LERF_OUT_U8_HWC 2  /* uint8 interleaved, the array the eval scripts save */
 
+/* fixed interpolation kernels of lerf_warp_fixed (resize_right/interp_methods.py:32-100; support in brackets) */
+#define LERF_WARP_NEAREST 0   /* box2d     (1)  NearestWarp2dNumpy   resize_right2d_numpy.py:460-467 */
+#define LERF_WARP_BILINEAR 1  /* linear2d  (2)  BilinearWarp2dNumpy  :469-476 */
+#define LERF_WARP_BICUBIC 2   /* cubic2d   (4)  BicubicWarp2dNumpy   :451-458 */
+#define LERF_WARP_LANCZOS2 3  /* lanczos2d (4)  Lanczos2Warp2dNumpy  :478-485 */
+#define LERF_WARP_LANCZOS3 4  /* lanczos3d (6)  Lanczos3Warp2dNumpy  :487-494 */
+
 typedef struct lerf_luts lerf_luts_t;       /* device-resident LUT set */
 typedef struct lerf_sr_plan lerf_sr_plan_t; /* device-resident SR geometry (set_shape) */
 typedef void* lerf_stream_t;                /* cudaStream_t */
@@ -169,6 +176,14 @@ int lerf_warp(int kind, const uint8_t* feat, const uint8_t* codes, int planes, i
 int lerf_warp_f32(int kind, const float* img, const float* h0, const float* h1, const float* h2, int planes,
                   int H, int W, int oH, int oW, const double minv[9], int pad0_y, int pad0_x,
                   float max_sigma, float* out, lerf_stream_t stream);
+
+/* Fixed-kernel warps, the baselines the reference compares LeRF with: Warp2dNumpy.warp
+ * (resize_right2d_numpy.py:409-449) with a separable kernel LERF_WARP_*.  img: DEVICE planar [P][H][W], float32 or
+ * (img_is_u8 != 0) uint8; out: DEVICE float32 planar [P][oH][oW]; pad0_y/pad0_x: leading pads for THIS kernel's support
+ * (lerf_warp_fixed_support(kernel)), from output pixel (0,0) only (:363-369).  NaN where the reference produces 0/0. */
+int lerf_warp_fixed_support(int kernel);
+int lerf_warp_fixed(int kernel, const void* img, int img_is_u8, int planes, int H, int W, int oH, int oW,
+                    const double minv[9], int pad0_y, int pad0_x, float* out, lerf_stream_t stream);
 
 /* ---- fused SR path ---------------------------------------------------------------------------------
  * Stage 1 + stage 2 + resampling + epilogue for a batch of images in one call: the body of

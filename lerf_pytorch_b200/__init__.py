@@ -12,7 +12,8 @@ from .pipeline import LerfSR, LerfWarp  # noqa: F401
 from .resize_right2d import (  # noqa: F401
     AmplifiedLinearResize2d, AmplifiedLinearResize2dNumpy, AmplifiedLinearResize2dTorch,
     AmplifiedLinearWarp2d, AmplifiedLinearWarp2dNumpy, AmplifiedLinearWarp2dTorch,
-    NearestWarp2d, NearestWarp2dNumpy, NearestWarp2dTorch,
+    BicubicWarp2d, BicubicWarp2dNumpy, BilinearWarp2d, BilinearWarp2dNumpy, Lanczos2Warp2d, Lanczos2Warp2dNumpy,
+    Lanczos3Warp2d, Lanczos3Warp2dNumpy, NearestWarp2d, NearestWarp2dNumpy, NearestWarp2dTorch,
     SteeringGaussianResize2d, SteeringGaussianResize2dNumpy, SteeringGaussianResize2dTorch,
     SteeringGaussianWarp2d, SteeringGaussianWarp2dNumpy, SteeringGaussianWarp2dTorch, sr_axis_tables)
 

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "liblerf_b200.so")
 
 LERF_KIND_GAUSS, LERF_KIND_LINEAR = 0, 1
 LERF_OUT_F32, LERF_OUT_U8, LERF_OUT_U8_HWC = 0, 1, 2
+LERF_WARP_NEAREST, LERF_WARP_BILINEAR, LERF_WARP_BICUBIC, LERF_WARP_LANCZOS2, LERF_WARP_LANCZOS3 = 0, 1, 2, 3, 4
 
 _c_i, _c_ll, _c_f, _c_p, _c_sz = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
 
@@ -38,6 +39,8 @@ PROTOTYPES = {
                          _c_p, _c_i, _c_i, _c_i, _c_p]),
     "lerf_warp_f32": (_c_i, [_c_i, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p, _c_i, _c_i, _c_f,
                              _c_p, _c_p]),
+    "lerf_warp_fixed_support": (_c_i, [_c_i]),
+    "lerf_warp_fixed": (_c_i, [_c_i, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p, _c_i, _c_i, _c_p, _c_p]),
     "lerf_sr_scratch_bytes": (_c_sz, [_c_i, _c_i, _c_i, _c_i]),
     "lerf_sr_fused": (_c_i, [_c_p, _c_i, _c_p, _c_p, _c_i, _c_i, _c_ll, _c_ll, _c_ll, _c_ll, _c_f, _c_i, _c_i, _c_p,
                              _c_p, _c_i, _c_p]),

@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "liblerf_b200.so")
-SOURCES = ["lut.cu", "lut_cell.cu", "resample.cu", "resample_int.cu", "resample_tile.cu", "fused.cu", "pipeline.cu"]
+SOURCES = ["lut.cu", "lut_cell.cu", "resample.cu", "resample_int.cu", "resample_tile.cu", "warp_fixed.cu", "fused.cu", "pipeline.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 

@@ -16,7 +16,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import LERF_KIND_GAUSS, LERF_KIND_LINEAR, LERF_OUT_F32, LERF_OUT_U8, LERF_OUT_U8_HWC
+from ._lib import (LERF_KIND_GAUSS, LERF_KIND_LINEAR, LERF_OUT_F32, LERF_OUT_U8, LERF_OUT_U8_HWC, LERF_WARP_BICUBIC,
+                   LERF_WARP_BILINEAR, LERF_WARP_LANCZOS2, LERF_WARP_LANCZOS3, LERF_WARP_NEAREST)
 
 _EPS = np.finfo(np.float32).eps  # resize_right2d_numpy.py:12
 _FMT = {"f32": LERF_OUT_F32, "u8": LERF_OUT_U8, "u8_hwc": LERF_OUT_U8_HWC}
@@ -349,8 +350,62 @@ class NearestWarp2d(Warp2d):
         return m
 
     def warp(self, input):
-        """Nearest-neighbour warp of an arbitrary image is only provided for the mask use case."""
-        raise NotImplementedError("NearestWarp2d.warp(image): use .mask(border) (eval_lut_warp.py:197-204)")
+        """Nearest-neighbour warp of an image (Warp2dNumpy.warp with box2d, :409-449, :460-467)."""
+        return _fixed_warp(self, LERF_WARP_NEAREST, input)
+
+
+def _fixed_warp(self, kernel, input):
+    """Warp2dNumpy.warp (:409-449) with a fixed separable kernel through lerf_warp_fixed: numpy [C,H,W] in -> numpy float32
+    out, torch CUDA [C,H,W] / [B,C,H,W] in -> torch float32 out; uint8 or float32 values."""
+    supp = _lib.lib().lerf_warp_fixed_support(kernel)
+    if self.support_sz != supp:
+        raise NotImplementedError("support_sz=%r: this kernel's support is %d" % (self.support_sz, supp))
+    dev = _cuda_device(input if isinstance(input, torch.Tensor) else None)
+    was_numpy = not isinstance(input, torch.Tensor)
+    t = torch.from_numpy(np.ascontiguousarray(input)) if was_numpy else input
+    is_u8 = t.dtype == torch.uint8
+    t = t.to(dev).contiguous() if is_u8 else t.to(device=dev, dtype=torch.float32).contiguous()
+    lead = tuple(t.shape[:-2])
+    H, W = int(t.shape[-2]), int(t.shape[-1])
+    if [H, W] != self.in_sz:
+        raise ValueError("input is %dx%d but set_shape() was given %dx%d" % (H, W, self.in_sz[0], self.in_sz[1]))
+    P = int(np.prod(lead)) if lead else 1
+    oH, oW = self.out_sz
+    out = torch.empty((P, oH, oW), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().lerf_warp_fixed(kernel, t.data_ptr(), 1 if is_u8 else 0, P, H, W, oH, oW, self.minv.ctypes.data,
+                                              self.pad0[0], self.pad0[1], out.data_ptr(), _stream_ptr(dev)))
+    out = out.reshape(lead + (oH, oW))
+    return out.cpu().numpy() if was_numpy else out
+
+
+class _FixedWarp2d(Warp2d):
+    """Bicubic / Bilinear / Lanczos2 / Lanczos3Warp2dNumpy (resize_right2d_numpy.py:451-494): the baselines of the paper."""
+
+    kernel = None
+    default_support = None
+
+    def __init__(self, support_sz=None, device="GPU", pad_mode="constant"):
+        super().__init__(self.default_support if support_sz is None else support_sz, device, pad_mode)
+
+    def warp(self, input):
+        return _fixed_warp(self, self.kernel, input)
+
+
+class BilinearWarp2d(_FixedWarp2d):
+    kernel, default_support = LERF_WARP_BILINEAR, 2
+
+
+class BicubicWarp2d(_FixedWarp2d):
+    kernel, default_support = LERF_WARP_BICUBIC, 4
+
+
+class Lanczos2Warp2d(_FixedWarp2d):
+    kernel, default_support = LERF_WARP_LANCZOS2, 4
+
+
+class Lanczos3Warp2d(_FixedWarp2d):
+    kernel, default_support = LERF_WARP_LANCZOS3, 6
 
 
 # The reference's names (numpy flavour is what the LUT eval scripts import; torch flavour = same API on [B,C,H,W])
@@ -359,3 +414,7 @@ AmplifiedLinearResize2dNumpy = AmplifiedLinearResize2dTorch = AmplifiedLinearRes
 SteeringGaussianWarp2dNumpy = SteeringGaussianWarp2dTorch = SteeringGaussianWarp2d
 AmplifiedLinearWarp2dNumpy = AmplifiedLinearWarp2dTorch = AmplifiedLinearWarp2d
 NearestWarp2dNumpy = NearestWarp2dTorch = NearestWarp2d
+BilinearWarp2dNumpy = BilinearWarp2d
+BicubicWarp2dNumpy = BicubicWarp2d
+Lanczos2Warp2dNumpy = Lanczos2Warp2d
+Lanczos3Warp2dNumpy = Lanczos3Warp2d

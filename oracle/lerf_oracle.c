@@ -464,3 +464,82 @@ int lerf_oracle_nearest_warp(const float* img, int C, int H, int W, const double
   }
   return 0;
 }
+
+/* ---------------------------------------------------------------------------
+ * Fixed-kernel warps: Bilinear / Bicubic / Lanczos2 / Lanczos3Warp2dNumpy
+ * (resize_right2d_numpy.py:451-494) = Warp2dNumpy.warp (:409-449) with the separable kernels of
+ * resize_right/interp_methods.py:32-100.  kernel: 0 box (support 1), 1 linear (2), 2 cubic (4),
+ * 3 lanczos2 (4), 4 lanczos3 (6).
+ * ------------------------------------------------------------------------- */
+static const double LERF_PI = 3.141592653589793;
+
+static inline double k_cubic(double x) { /* interp_methods.py:32-41 */
+  const double a = fabs(x), a2 = a * a, a3 = a * a * a;
+  double r = 0.0;
+  if (a <= 1.0) r += 1.5 * a3 - 2.5 * a2 + 1.0;
+  if (1.0 < a && a <= 2.0) r += -0.5 * a3 + 2.5 * a2 - 4.0 * a + 2.0;
+  return r;
+}
+static inline double k_lanczos(double x, double n) { /* :44-55: ((sin(pi x) sin(pi x / n) + eps) / (pi^2 x^2 / n + eps)) [|x| < n] */
+  const double v = (sin(LERF_PI * x) * sin(LERF_PI * x / n) + EPS32) / ((LERF_PI * LERF_PI * x * x / n) + EPS32);
+  return fabs(x) < n ? v : 0.0;
+}
+static inline double k_linear(double x) { /* :58-62 */
+  return (x + 1.0) * (double)((-1.0 <= x) && (x < 0.0)) + (1.0 - x) * (double)((0.0 <= x) && (x <= 1.0));
+}
+static inline double k_box(double x) { /* :65-68 */
+  return (double)((-1.0 <= x) && (x < 0.0)) + (double)((0.0 <= x) && (x <= 1.0));
+}
+static inline double k_eval(int kernel, double x) {
+  switch (kernel) {
+    case 0: return k_box(x);
+    case 1: return k_linear(x);
+    case 2: return k_cubic(x);
+    case 3: return k_lanczos(x, 2.0);
+    default: return k_lanczos(x, 3.0);
+  }
+}
+
+int lerf_oracle_fixed_warp_support(int kernel) {
+  static const int S[5] = {1, 2, 4, 4, 6};
+  return (kernel < 0 || kernel > 4) ? -1 : S[kernel];
+}
+
+int lerf_oracle_fixed_warp(int kernel, const float* img, int C, int H, int W, const double* minv,
+                           int oH, int oW, double* out) {
+  const int supp = lerf_oracle_fixed_warp_support(kernel);
+  if (supp < 0) return 1;
+  int p0x, p0y;
+  warp_pads(minv, H, W, oH, oW, supp, &p0x, &p0y);
+#pragma omp parallel for schedule(static)
+  for (int ox = 0; ox < oH; ++ox) {
+    for (int oy = 0; oy < oW; ++oy) {
+      double px, py;
+      warp_project(minv, ox, oy, H, W, &px, &py);
+      const int lx = warp_left(px, supp) + p0x, ly = warp_left(py, supp) + p0y; /* :366 */
+      px += (double)p0x; py += (double)p0y;                                      /* :367 */
+      double wx[6], wy[6];
+      int sx[6], sy[6];
+      for (int k = 0; k < supp; ++k) {
+        const int fx = clampi(lx + k, 0, H - 1), fy = clampi(ly + k, 0, W - 1);  /* :397-398 */
+        wx[k] = k_eval(kernel, px - (double)fx);                                 /* :400-403, weight(dis_x, dis_y) */
+        wy[k] = k_eval(kernel, py - (double)fy);
+        sx[k] = fx - p0x; sy[k] = fy - p0y;                                      /* index into the un-padded image */
+      }
+      /* patch element (i, j): row tap j, column tap i (the meshgrid of :357 is 'xy'); sum over the patch (:428) */
+      double s = 0.0;
+      for (int i = 0; i < supp; ++i)
+        for (int j = 0; j < supp; ++j) s += wx[j] * wy[i];
+      for (int c = 0; c < C; ++c) {
+        double acc = 0.0;
+        for (int i = 0; i < supp; ++i)
+          for (int j = 0; j < supp; ++j) {
+            const double v = (sx[j] >= 0 && sy[i] >= 0) ? (double)img[((size_t)c * H + sx[j]) * W + sy[i]] : 0.0;
+            acc += v * ((wx[j] * wy[i]) / s);                                    /* :431, :446-447 */
+          }
+        out[((size_t)c * oH + ox) * oW + oy] = acc;
+      }
+    }
+  }
+  return 0;
+}

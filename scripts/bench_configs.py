@@ -107,6 +107,19 @@ def cfg4():
                "(stages + mask + warp, output allocated per call)" % (canvas, canvas), tot / 8, img.numel(), outs // 8)
 
 
+def fixed():
+    """Fixed-kernel warps on the cfg-4 in-scale geometry: 1024x1024 uint8 -> 3072x3072 float32."""
+    img = natural(1, 1024, 1024, 4000)[0].permute(2, 0, 1).contiguous()
+    M = np.array([[3.0, 0.2, 10.0], [-0.15, 2.9, 20.0], [1e-4, -2e-4, 1.0]])
+    for cls in (lp.NearestWarp2dNumpy, lp.BilinearWarp2dNumpy, lp.BicubicWarp2dNumpy, lp.Lanczos2Warp2dNumpy, lp.Lanczos3Warp2dNumpy):
+        rs = cls()
+        rs.set_shape([3, 1024, 1024], M, (3, 3072, 3072))
+        out = rs.warp(img)
+        ms = timeit(lambda: rs.warp(img), 10)
+        report("fixed/" + cls.__name__, "fixed-kernel warp 1024x1024 -> 3072x3072, support %d, float64 weights" % rs.support_sz, ms,
+               img.numel(), out.numel())
+
+
 def cfg5():
     luts = lp.LutSet(lp.load_lut_dict(os.path.join(LUTS, "lerf-g")), device=dev)
     img = natural(1, 2160, 3840, 5000)[0]

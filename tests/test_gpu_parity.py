@@ -572,6 +572,41 @@ def test_fast_warp_kernel_vs_float64_kernel(lp, orc, luts):
             lp.lib().lerf_debug_warp_records(1)
 
 
+def test_fixed_kernel_warps_vs_reference_goldens_and_oracle(lp, orc):
+    """Nearest / Bilinear / Bicubic / Lanczos2 / Lanczos3Warp2dNumpy through lerf_warp_fixed against the
+    reference's own outputs (tests/golden/fixed_warp.npz, warp.npz) and, on a larger case, against the oracle."""
+    g, w = golden("fixed_warp"), golden("warp")
+    img_u8 = w["img"]
+    img = img_u8.astype(np.float32)
+    oshape = tuple(int(v) for v in g["out_shape"])
+    names = (("bilinear", lp.BilinearWarp2dNumpy, orc.BilinearWarp2dNumpy), ("bicubic", lp.BicubicWarp2dNumpy, orc.BicubicWarp2dNumpy),
+             ("lanczos2", lp.Lanczos2Warp2dNumpy, orc.Lanczos2Warp2dNumpy), ("lanczos3", lp.Lanczos3Warp2dNumpy, orc.Lanczos3Warp2dNumpy))
+    worst = 0.0
+    for i in g["which"]:
+        for name, cls, _ in names:
+            rs = cls()
+            rs.set_shape(img.shape, w["mats"][i], oshape)
+            assert rs.pad0 == (int(g["pad_%s_%d" % (name, i)][1][0]), int(g["pad_%s_%d" % (name, i)][2][0]))
+            out = rs.warp(img)                      # numpy in -> numpy out, like the reference
+            assert isinstance(out, np.ndarray) and out.shape == oshape
+            worst = max(worst, _maxabs(out, g["%s_%d" % (name, i)]))
+            out8 = rs.warp(_cuda(img_u8))           # uint8 CUDA tensor in -> CUDA tensor out, same values
+            assert torch.equal(out8.cpu(), torch.from_numpy(out))
+    for i, M in enumerate(w["mats"]):               # nearest: the goldens of warp.npz (values are copied, so exact)
+        nn = lp.NearestWarp2dNumpy()
+        nn.set_shape(img.shape, M, tuple(int(v) for v in w["out_shape"]))
+        assert _maxabs(nn.warp(img), w["nearest_%d" % i]) == 0.0
+    print("fixed-kernel warps: worst max-abs error vs the reference goldens %.3g" % worst)
+    assert worst <= FP32_TOL
+    big = uniform_image(611, 96, 80).transpose(2, 0, 1).astype(np.float32)
+    M = np.array([[2.6, 0.3, 12.0], [-0.25, 3.1, 9.0], [3e-4, -2e-4, 1.0]])
+    for name, cls, ocls in names:
+        rs, ro = cls(), ocls()
+        rs.set_shape(big.shape, M, (3, 300, 280))
+        ro.set_shape(big.shape, M, (3, 300, 280))
+        assert _maxabs(rs.warp(big), ro.warp(big)) <= FP32_TOL, name
+
+
 def test_extreme_hypers_no_nan(lp):
     """All-taps-underflow hazard: sigma = max everywhere, rho = +-1, far taps -> weights ~ 2^-288."""
     H, W = 12, 14

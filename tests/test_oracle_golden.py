@@ -127,6 +127,20 @@ def test_warp_matches_reference_float64():
         assert np.array_equal(orc.warp_mask(img.shape, M, oshape), g["mask_%d" % i]), i
 
 
+def test_fixed_kernel_warps_match_reference_float64():
+    """Bilinear / Bicubic / Lanczos2 / Lanczos3Warp2dNumpy goldens (tests/golden/make_golden_fixed.py)."""
+    g = golden("fixed_warp")
+    w = golden("warp")
+    img = w["img"].astype(np.float32)
+    oshape = tuple(int(v) for v in g["out_shape"])
+    for i in g["which"]:
+        for name, cls in (("bilinear", orc.BilinearWarp2dNumpy), ("bicubic", orc.BicubicWarp2dNumpy),
+                          ("lanczos2", orc.Lanczos2Warp2dNumpy), ("lanczos3", orc.Lanczos3Warp2dNumpy)):
+            rs = cls()
+            rs.set_shape(img.shape, w["mats"][i], oshape)
+            assert _maxabs(rs.warp(img), g["%s_%d" % (name, i)]) < 1e-9, (name, i)
+
+
 def test_whole_path_set5():
     g = golden("set5_path")
     st = golden("lut_stages")
