@@ -44,7 +44,74 @@ def build_parser(description, default_test_dir):
     p.add_argument('--device', type=str, default='cuda:0')
     p.add_argument('--no-save', dest='save', action='store_false', default=True,
                    help='skip writing PNG / npy results (metrics only)')
+    p.add_argument('--io-threads', dest='io_threads', type=int, default=4,
+                   help='host threads that decode the next images and encode / score finished ones while the GPU works '
+                        '(SURVEY.md 8f item 2); 0 = everything inline like the reference')
     return p
+
+
+class IoPipeline(object):
+    """The image I/O step either side of the hot path (reference: PIL decode eval_lut_sr.py:517-534,
+    PNG / npy writes :667-708, metrics :735-742, all inline on one thread).
+
+    ``prefetch(load, items)`` yields ``load(item)`` in order while up to ``depth`` later items are being decoded on worker
+    threads; ``submit(fn, *args)`` runs encodes / metrics on the same workers and returns a future; ``drain()`` waits
+    for everything submitted and re-raises the first failure.  PIL's zlib work releases the GIL, so the workers run
+    in parallel with each other and with the CUDA launches of the main thread.  With ``threads=0`` every call runs
+    inline, which is the reference's behaviour.
+    """
+
+    def __init__(self, threads=4, depth=None):
+        self.threads = max(0, int(threads))
+        self.depth = max(1, self.threads if depth is None else depth)
+        self._pool = None
+        self._pending = []
+        if self.threads:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=self.threads, thread_name_prefix="lerf-io")
+
+    def prefetch(self, load, items):
+        items = list(items)
+        if not self._pool:
+            for it in items:
+                yield load(it)
+            return
+        futs = []
+        nxt = 0
+        for i in range(len(items)):
+            while nxt < len(items) and nxt <= i + self.depth:
+                futs.append(self._pool.submit(load, items[nxt]))
+                nxt += 1
+            yield futs[i].result()
+            futs[i] = None  # drop the decoded image as soon as it is consumed
+
+    def submit(self, fn, *args):
+        if not self._pool:
+            return _Done(fn(*args))
+        f = self._pool.submit(fn, *args)
+        self._pending.append(f)
+        return f
+
+    def drain(self):
+        pending, self._pending = self._pending, []
+        for f in pending:
+            f.result()
+
+    def close(self):
+        try:
+            self.drain()
+        finally:
+            if self._pool:
+                self._pool.shutdown(wait=True)
+                self._pool = None
+
+
+class _Done(object):
+    def __init__(self, value):
+        self._value = value
+
+    def result(self):
+        return self._value
 
 
 def check_supported(opt):

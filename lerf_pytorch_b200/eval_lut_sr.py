@@ -16,7 +16,7 @@ import sys
 import numpy as np
 
 from . import metrics
-from .eval_common import build_parser, check_supported, list_pngs, load_lut_dict_like_reference, load_rgb
+from .eval_common import IoPipeline, build_parser, check_supported, list_pngs, load_lut_dict_like_reference, load_rgb
 
 
 class Evaluator(object):
@@ -40,19 +40,28 @@ class Evaluator(object):
         return self._sr[key]
 
     def run(self, dataset, scale_h, scale_w):
+        """One dataset at one scale.  Decode (next images), GPU work (this image) and encode + metrics (previous images)
+        overlap through an IoPipeline; results come back in file order."""
         opt = self.opt
         files = list_pngs(os.path.join(opt.testDir, dataset, "HR"))
         result_path = os.path.join(opt.resultRoot, opt.expDir.rstrip("/").split("/")[-1],
                                    "X{:.2f}_{:.2f}".format(scale_h, scale_w), dataset)
         if opt.save and not os.path.isdir(result_path):
             os.makedirs(result_path)
-        return [self._worker(dataset, f, scale_h, scale_w, result_path) for f in files]
+        io = IoPipeline(getattr(opt, "io_threads", 0))
+        try:
+            def load(fname):
+                lr = load_rgb(os.path.join(opt.testDir, dataset, "LR_bicubic/rrLR_X{:.2f}_{:.2f}".format(scale_h, scale_w), fname))
+                return fname, lr, load_rgb(os.path.join(opt.testDir, dataset, "HR", fname))
 
-    def _worker(self, dataset, fname, scale_h, scale_w, result_path):
-        from PIL import Image
+            scores = [self._worker(io, fname, lr, gt, scale_h, scale_w, result_path) for fname, lr, gt in io.prefetch(load, files)]
+            io.drain()
+            return [f.result() for f in scores]
+        finally:
+            io.close()
+
+    def _worker(self, io, fname, img_lr, img_gt, scale_h, scale_w, result_path):
         opt, torch = self.opt, self.torch
-        img_lr = load_rgb(os.path.join(opt.testDir, dataset, "LR_bicubic/rrLR_X{:.2f}_{:.2f}".format(scale_h, scale_w), fname))
-        img_gt = load_rgb(os.path.join(opt.testDir, dataset, "HR", fname))
         sr = self.engine(scale_h, scale_w)
         with torch.cuda.device(self.device):
             d_in = torch.from_numpy(np.ascontiguousarray(img_lr.astype(np.uint8))).to(self.device)
@@ -63,11 +72,16 @@ class Evaluator(object):
                 img_hyper = codes.cpu().numpy().astype(np.float32) / float(255)  # :623-628
         if opt.save:
             stem = fname.split("/")[-1][:-4]
-            Image.fromarray(img_out).save(os.path.join(result_path, "{}_{}.png".format(stem, opt.lutName)))
-            Image.fromarray(np.ascontiguousarray(feat.transpose((1, 2, 0)))).save(os.path.join(result_path, "{}_lr.png".format(stem)))
-            Image.fromarray(img_gt).save(os.path.join(result_path, "{}_gt.png".format(stem)))
-            np.save(os.path.join(result_path, "{}_{}_hyper.npy".format(fname.split("_")[-1][:-4], opt.lutName)), img_hyper)
-        return metrics.psnr_y_ssim(img_gt, img_out, scale_h, scale_w)
+            io.submit(_save_png, img_out, os.path.join(result_path, "{}_{}.png".format(stem, opt.lutName)))
+            io.submit(_save_png, np.ascontiguousarray(feat.transpose((1, 2, 0))), os.path.join(result_path, "{}_lr.png".format(stem)))
+            io.submit(_save_png, img_gt, os.path.join(result_path, "{}_gt.png".format(stem)))
+            io.submit(np.save, os.path.join(result_path, "{}_{}_hyper.npy".format(fname.split("_")[-1][:-4], opt.lutName)), img_hyper)
+        return io.submit(metrics.psnr_y_ssim, img_gt, img_out, scale_h, scale_w)
+
+
+def _save_png(arr, path):
+    from PIL import Image
+    Image.fromarray(arr).save(path)
 
 
 def format_table(all_datasets, all_scales, results):

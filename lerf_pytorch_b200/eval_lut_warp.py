@@ -12,7 +12,7 @@ import sys
 import numpy as np
 
 from . import metrics
-from .eval_common import build_parser, check_supported, list_pngs, load_lut_dict_like_reference, load_rgb
+from .eval_common import IoPipeline, build_parser, check_supported, list_pngs, load_lut_dict_like_reference, load_rgb
 
 
 class Evaluator(object):
@@ -29,37 +29,52 @@ class Evaluator(object):
         self.warp = LerfWarp(self.luts, max_sigma=opt.maxSigma, support_sz=opt.suppSize, border=self.border)
 
     def run(self, dataset, scale_p):
-        opt = self.opt
+        """One dataset at one scale class; decode / GPU work / encode + metrics overlap through an IoPipeline."""
+        opt, torch = self.opt, self.torch
         files = list_pngs(os.path.join(opt.testDir, dataset, "HR"))
         result_path = os.path.join(opt.resultRoot, opt.expDir.rstrip("/").split("/")[-1], dataset, scale_p)
         if opt.save and not os.path.isdir(result_path):
             os.makedirs(result_path)
-        return [self._worker(dataset, scale_p, f, result_path) for f in files]
+        io = IoPipeline(getattr(opt, "io_threads", 0))
+        try:
+            def load(fname):
+                lr = load_rgb(os.path.join(opt.testDir, dataset, scale_p, fname))
+                matrix = torch.load(os.path.join(opt.testDir, dataset, scale_p, fname.replace("png", "pth"))).numpy()
+                return fname, lr, matrix, load_rgb(os.path.join(opt.testDir, dataset, "HR", fname))
 
-    def _worker(self, dataset, scale_p, fname, result_path):
-        from PIL import Image
+            scores = [self._worker(io, fname, lr, m, gt, result_path) for fname, lr, m, gt in io.prefetch(load, files)]
+            io.drain()
+            return [f.result() for f in scores]
+        finally:
+            io.close()
+
+    def _worker(self, io, fname, img_lr, matrix, img_gt, result_path):
         opt, torch = self.opt, self.torch
-        img_lr = load_rgb(os.path.join(opt.testDir, dataset, scale_p, fname))
-        matrix = torch.load(os.path.join(opt.testDir, dataset, scale_p, fname.replace("png", "pth"))).numpy()
-        img_gt = load_rgb(os.path.join(opt.testDir, dataset, "HR", fname))
         with torch.cuda.device(self.device):
             d_in = torch.from_numpy(np.ascontiguousarray(img_lr.astype(np.uint8))).to(self.device)
             out, mask = self.warp(d_in, matrix, img_gt.shape[:2], out_format="u8_hwc", with_mask=True)
             img_out = out.cpu().numpy()
             valid = mask.cpu().numpy().astype(bool)                        # mask_output == 255 (:229)
+            feat = None
             if opt.save:
                 from .lut_interp import lut_stage1
                 feat = lut_stage1(self.luts, d_in, "HWC").cpu().numpy()
-        valid3 = np.repeat(valid[:, :, None], img_gt.shape[2], axis=2)
-        mpsnr = metrics.mpsnr(img_out, img_gt, valid3)                      # :226-233
-        if opt.save:
-            stem = fname.split("/")[-1][:-4]
-            Image.fromarray(np.ascontiguousarray(feat.transpose((1, 2, 0)))).save(os.path.join(result_path, "{}_lr.png".format(stem)))
-            Image.fromarray((valid3 * 255).astype(np.uint8)).save(os.path.join(result_path, "{}_mask.png".format(stem)))
-            white = (np.ones_like(img_gt) * 255).astype(np.uint8)          # non valid pixels leave as white (:259-261)
-            Image.fromarray(img_out * valid3 + (~valid3) * white).save(os.path.join(result_path, "{}_{}.png".format(stem, opt.lutName)))
-            Image.fromarray(img_gt * valid3 + (~valid3) * white).save(os.path.join(result_path, "{}_gt.png".format(stem)))
-        return [mpsnr]
+        return io.submit(_score_and_save, img_out, img_gt, valid, feat, fname, result_path, opt.lutName, opt.save)
+
+
+def _score_and_save(img_out, img_gt, valid, feat, fname, result_path, lut_name, save):
+    """Host side of eltr._worker after the warp (eval_lut_warp.py:226-261): mPSNR inside the mask, then the four PNGs."""
+    from PIL import Image
+    valid3 = np.repeat(valid[:, :, None], img_gt.shape[2], axis=2)
+    mpsnr = metrics.mpsnr(img_out, img_gt, valid3)                          # :226-233
+    if save:
+        stem = fname.split("/")[-1][:-4]
+        Image.fromarray(np.ascontiguousarray(feat.transpose((1, 2, 0)))).save(os.path.join(result_path, "{}_lr.png".format(stem)))
+        Image.fromarray((valid3 * 255).astype(np.uint8)).save(os.path.join(result_path, "{}_mask.png".format(stem)))
+        white = (np.ones_like(img_gt) * 255).astype(np.uint8)              # non valid pixels leave as white (:259-261)
+        Image.fromarray(img_out * valid3 + (~valid3) * white).save(os.path.join(result_path, "{}_{}.png".format(stem, lut_name)))
+        Image.fromarray(img_gt * valid3 + (~valid3) * white).save(os.path.join(result_path, "{}_gt.png".format(stem)))
+    return [mpsnr]
 
 
 def format_table(all_datasets, all_scales, results):
