@@ -32,6 +32,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=None)
     args = ap.parse_args()
     rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")  # stdout carries only the JSON line; NCCL's version banner on fd 1 goes to stderr
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
@@ -80,7 +83,7 @@ def main():
     if rank == 0:
         peak, src = bench.measured_peak_gbs()
         byt = C * H * W + C * oH * oW * 4
-        print(json.dumps({
+        json_out.write(json.dumps({
             "metric": "output MPix/s (LeRF-G x8 SR, one 3840x2160 frame, row-band sharded)", "value": oH * oW / 1e6 / (ms * 1e-3),
             "unit": "MPix/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong", "data": "synthetic",
@@ -90,7 +93,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": byt / (ms * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s",
                          "frac": byt / (ms * 1e-3) / 1e9 / world / peak, "peak_source": src,
                          "note": "whole path, algorithmic bytes C*H*W + 4*C*oH*oW, per GPU"},
-            "band_equals_halo_crop_on_every_rank": bool(flag.item())}))
+            "band_equals_halo_crop_on_every_rank": bool(flag.item())}) + "\n")
+        json_out.flush()
     if dist is not None:
         dist.destroy_process_group()
     return 0 if ok else 1
