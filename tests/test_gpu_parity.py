@@ -607,6 +607,37 @@ def test_fixed_kernel_warps_vs_reference_goldens_and_oracle(lp, orc):
         assert _maxabs(rs.warp(big), ro.warp(big)) <= FP32_TOL, name
 
 
+@pytest.mark.parametrize("hw", [(1, 1), (2, 3), (3, 2), (5, 1), (1, 7), (4, 4), (33, 31)])
+def test_tiny_and_ragged_images_vs_oracle(lp, orc, luts, hw):
+    """Edge cases: images smaller than every tile, halo and tap window (all taps clamp), odd sizes, one-pixel rows/columns."""
+    img = uniform_image(700 + 10 * hw[0] + hw[1], hw[0], hw[1])
+    for model, scales in (("g", ((2, 2), (4, 4), (1.5, 2.5), (8, 8))), ("l", ((2, 2), (3.5, 3.5)))):
+        ld, ls = luts[model]
+        for sh, sw in scales:
+            ref, rfeat, rcodes = orc.lerf_sr(img, ld, sh, sw, linear=(model == "l"))
+            sr = lp.LerfSR(ls, sh, sw)
+            out = sr(_cuda(img), out_format="f32").cpu().numpy()
+            feat, codes = sr.stages(_cuda(img))
+            assert np.array_equal(feat.cpu().numpy(), rfeat) and np.array_equal(codes.cpu().numpy(), rcodes), (model, sh, sw)
+            assert out.shape == ref.shape
+            assert _maxabs(out, ref) <= FP32_TOL, (model, sh, sw)
+            u8 = sr(_cuda(img), out_format="u8_hwc").cpu().numpy()
+            assert np.max(np.abs(u8.astype(int) - orc.to_uint8_hwc(ref).astype(int))) <= 1
+
+
+def test_empty_inputs_are_accepted(lp, luts):
+    """Zero planes / empty row bands are no-ops with status 0, not errors (the C ABI's contract for ragged work lists)."""
+    _, ls = luts["g"]
+    sr = lp.LerfSR(ls, 4)
+    img = _cuda(uniform_image(5, 16, 12))
+    full = sr(img, out_format="f32")
+    out = torch.full_like(full, -1.0)
+    sr(img, out_format="f32", rows=(7, 7), out=out.unsqueeze(0))   # empty band: nothing written
+    assert float(out.max()) == -1.0
+    L = lp.lib()
+    assert L.lerf_lut_stage2(ls.handle, img.data_ptr(), 0, 16, 12, 0, 16, img.data_ptr(), None) == 0
+
+
 def test_extreme_hypers_no_nan(lp):
     """All-taps-underflow hazard: sigma = max everywhere, rho = +-1, far taps -> weights ~ 2^-288."""
     H, W = 12, 14
