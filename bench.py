@@ -429,10 +429,22 @@ def main():
             dist.all_reduce(t2, op=dist.ReduceOp.MAX)
         ms2 = float(t2.item()) / args.e2e_steps
         chk = int(host_out[0, oH // 2, oW // 2].sum())  # touch the result on the host
+        # what the D2H link alone delivers for the same bytes (one plain pinned copy): the ceiling of this e2e figure
+        dbuf = torch.empty((B, oH, oW, C), dtype=torch.uint8, device=dev)
+        host_out.copy_(dbuf, non_blocking=True)
+        torch.cuda.synchronize()
+        a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a2.record()
+        host_out.copy_(dbuf, non_blocking=True)
+        b2.record()
+        torch.cuda.synchronize()
+        link_gbs = dbuf.numel() / (a2.elapsed_time(b2) * 1e-3) / 1e9
+        del dbuf
         e2e = {"value": n_gpus * out_mpix_step / (ms2 * 1e-3), "unit": "MPix/s", "h2d_bytes_per_step": B * H * W * C,
                "d2h_bytes_per_step": B * oH * oW * C, "ms_per_step": ms2, "steps": args.e2e_steps,
-               "api": "LerfSR.run_host(pinned uint8 HWC in, pinned uint8 HWC out), 3-stream pipeline", "checksum": chk,
-               "cpu_binding": cpu_binding}
+               "api": "LerfSR.run_host(pinned uint8 HWC in, pinned uint8 HWC out), 3 streams x 4 row bands per frame", "checksum": chk,
+               "cpu_binding": cpu_binding, "d2h_link_GBps_plain_copy": link_gbs,
+               "d2h_GBps_achieved": B * oH * oW * C / (ms2 * 1e-3) / 1e9}
     except Exception as ex:  # pragma: no cover
         e2e = {"value": None, "error": repr(ex)}
 

@@ -113,11 +113,14 @@ class LerfSR(object):
                                                 out.data_ptr(), _FMT[out_format], _stream_ptr(dev)))
         return out[0] if squeeze else out
 
-    def run_host(self, host_in, host_out, depth=3):
+    def run_host(self, host_in, host_out, depth=3, bands=4):
         """Host-to-host entry: ``host_in`` pinned uint8 [B,H,W,C], ``host_out`` pinned uint8 [B,oH,oW,C].
 
-        Frames are pipelined over ``depth`` streams (H2D copy, the three kernels, D2H copy per frame) so PCIe
-        transfers overlap compute.  Returns after everything has landed in ``host_out``.
+        Frames are pipelined over ``depth`` streams (H2D copy, the three kernels, D2H copy) so PCIe transfers overlap
+        compute; each frame is produced in ``bands`` output row bands (``rows=`` of ``__call__``: the stages run on
+        the band's input rows + halo), so the first device-to-host copy starts after a quarter of a frame's compute
+        instead of a whole frame's -- the path is bound by the D2H link and that start-up is all that is not hidden.
+        Returns after everything has landed in ``host_out``.
         """
         B, H, W, C = host_in.shape
         self.set_shape(H, W, C)
@@ -130,6 +133,8 @@ class LerfSR(object):
                               torch.empty((oH, oW, C), dtype=torch.uint8, device=dev)))
             self._slots = ((H, W, C, depth), slots)
         slots = self._slots[1]
+        nb = max(1, min(int(bands), oH // 256))
+        edges = [oH * k // nb for k in range(nb + 1)]
         cur = torch.cuda.current_stream(dev)
         for st, _, _ in slots:
             st.wait_stream(cur)
@@ -137,8 +142,10 @@ class LerfSR(object):
             st, d_in, d_out = slots[i % depth]
             with torch.cuda.stream(st):
                 d_in.copy_(host_in[i], non_blocking=True)
-                self(d_in, out_format="u8_hwc", out=d_out.unsqueeze(0), slot=1 + i % depth)
-                host_out[i].copy_(d_out, non_blocking=True)
+                for k in range(nb):
+                    r0, r1 = edges[k], edges[k + 1]
+                    self(d_in, out_format="u8_hwc", out=d_out.unsqueeze(0), slot=1 + i % depth, rows=(r0, r1))
+                    host_out[i, r0:r1].copy_(d_out[r0:r1], non_blocking=True)
         for st, _, _ in slots:
             cur.wait_stream(st)
         cur.synchronize()

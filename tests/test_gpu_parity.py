@@ -638,6 +638,21 @@ def test_empty_inputs_are_accepted(lp, luts):
     assert L.lerf_lut_stage2(ls.handle, img.data_ptr(), 0, 16, 12, 0, 16, img.data_ptr(), None) == 0
 
 
+@pytest.mark.parametrize("hw,scale", [((300, 200), 4), ((40, 56), 3.5)])
+def test_run_host_equals_device_path(lp, luts, hw, scale):
+    """The host-to-host entry (pinned buffers, 3 streams, row-band pipelining) returns exactly what the device path does."""
+    _, ls = luts["g"]
+    imgs = np.stack([uniform_image(810 + i, hw[0], hw[1]) for i in range(5)])
+    sr = lp.LerfSR(ls, scale)
+    want = sr(_cuda(imgs), out_format="u8_hwc").cpu()
+    host_in = torch.from_numpy(imgs).pin_memory()
+    host_out = torch.zeros(tuple(want.shape), dtype=torch.uint8).pin_memory()
+    for _ in range(2):  # the second call reuses the slots
+        host_out.zero_()
+        sr.run_host(host_in, host_out)
+        assert torch.equal(host_out, want)
+
+
 def test_extreme_hypers_no_nan(lp):
     """All-taps-underflow hazard: sigma = max everywhere, rho = +-1, far taps -> weights ~ 2^-288."""
     H, W = 12, 14
