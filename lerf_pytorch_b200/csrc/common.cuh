@@ -78,6 +78,7 @@ struct lerf_sr_plan_impl {
   int ph_y, ph_x;  // periodic geometry: the outputs whose first tap is l are S*l + ph + m, m = 0..S-1
   double ph_dist_y[8][2], ph_dist_x[8][2];  // their distances to tap 0 / tap 1
   int tile_ok;     // every 32 x 32 output group has its taps in a 33 x 33 input window (any scale >= 1), |dist| <= 1: resample_tile.cu
+  int tile_rows;   // output rows per block of the tile kernel: the largest of 128, 96, 64, 32 whose taps fit 33 input rows
   void* coef_dev;    // rsi::CoefTabs for coef_sigma (resample_int.cu), allocated on first use
   void* coef_host;
   float coef_sigma;

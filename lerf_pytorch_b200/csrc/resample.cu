@@ -362,6 +362,15 @@ int lerf_sr_plan_create(int H, int W, int oH, int oW, const int32_t* left_y, con
     lerf_sr_plan_destroy(reinterpret_cast<lerf_sr_plan_t*>(P));
     return fail(LERF_ECUDA, "lerf_sr_plan_create: upload failed: %s", cudaGetErrorString(e));
   }
+  P->tile_rows = 32;
+  for (int R : {128, 96, 64}) {
+    bool ok = true;
+    for (int o = 0; o < oH && ok; ++o) ok = left_y[o + R - 1 < oH ? o + R - 1 : oH - 1] - left_y[o] <= 31;
+    if (ok) {
+      P->tile_rows = R;
+      break;
+    }
+  }
   P->h_left_y = (int*)malloc(sizeof(int) * oH);
   memcpy(P->h_left_y, left_y, sizeof(int) * oH);
   const int sy = detect_int_scale(H, oH, left_y, dist_y, P->ph_y, P->ph_dist_y);

@@ -27,9 +27,10 @@ using namespace rsi;
 
 namespace {
 
-constexpr int kOX = 32, kOY = 32;            // outputs per block; 256 threads, thread (tx, ty) owns rows ty + 8 j
+constexpr int kOX = 32;             // output columns per block; 256 threads, thread (tx, ty) owns rows ty + 8 j of the block
 constexpr int kTY = 8;
-constexpr int kWX = kOX + 1, kWY = kOY + 1;  // input window capacity
+constexpr int kWX = 33, kWY = 33;   // input window capacity; a block covers as many output rows (32 .. 128, plan->tile_rows)
+                                    // as keep its taps inside 33 input rows, so the per-block set-up is amortised
 
 struct FixQ {
   double magic;     // 2^(52-FB) + 16 * 2^-FB
@@ -87,12 +88,12 @@ __global__ void __launch_bounds__(kOX* kTY)
     resize_sr_tile_kernel(const uint8_t* __restrict__ feat, const uint8_t* __restrict__ codes, int H, int W, int oH, int oW,
                           const int* __restrict__ left_y, const double* __restrict__ dist_y, const int* __restrict__ left_x,
                           const double* __restrict__ dist_x, const CoefTabs* __restrict__ ct, const FixQ fq, float max_sigma,
-                          int channels, int oy0, int oy1, void* __restrict__ out) {
+                          int channels, int oy0, int oy1, int rows_per_block, void* __restrict__ out) {
   __shared__ typename std::conditional<KIND == LERF_KIND_GAUSS, SmemG, SmemL>::type sm;
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   const int p = blockIdx.z;
   const int ox_first = blockIdx.x * kOX, ox_last = min(ox_first + kOX - 1, oW - 1);
-  const int oy_first = oy0 + blockIdx.y * kOY, oy_last = min(oy_first + kOY - 1, oy1 - 1);
+  const int oy_first = oy0 + blockIdx.y * rows_per_block, oy_last = min(oy_first + rows_per_block - 1, oy1 - 1);
   const int r0 = __ldg(left_y + oy_first), c0 = __ldg(left_x + ox_first);
   const int nr = __ldg(left_y + oy_last) - r0 + 2, nc = __ldg(left_x + ox_last) - c0 + 2;  // <= kWY, kWX (checked by the host)
   const long long plane_sz = (long long)H * W;
@@ -396,10 +397,11 @@ int resize_sr_tile(int kind, const lerf_sr_plan_impl* P, const uint8_t* feat, co
     ct = plan_coef_tabs(P, max_sigma, st);
     if (!ct) return fail(LERF_ECUDA, "uploading the hyper decode tables failed");
   }
-  dim3 block(kOX * kTY), grid((P->oW + kOX - 1) / kOX, (oy1 - oy0 + kOY - 1) / kOY, planes);
+  const int rpb = P->tile_rows;
+  dim3 block(kOX * kTY), grid((P->oW + kOX - 1) / kOX, (oy1 - oy0 + rpb - 1) / rpb, planes);
 #define LERF_GK(K, F, CL)                                                                                                 \
   resize_sr_tile_kernel<K, F, CL><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, P->left_y, P->dist_y,   \
-                                                          P->left_x, P->dist_x, ct, fq, max_sigma, channels, oy0, oy1, out)
+                                                          P->left_x, P->dist_x, ct, fq, max_sigma, channels, oy0, oy1, rpb, out)
 #define LERF_GO(F)                                                  \
   if (kind == LERF_KIND_GAUSS) LERF_GK(LERF_KIND_GAUSS, F, false);   \
   else if (max_sigma > 1.0f) LERF_GK(LERF_KIND_LINEAR, F, true);    \

@@ -107,6 +107,22 @@ def cfg4():
                "(stages + mask + warp, output allocated per call)" % (canvas, canvas), tot / 8, img.numel(), outs // 8)
 
 
+def tile():
+    """The tile kernel on Gaussian (LeRF-G) non-integer scales, 8 frames 2040x1356, against the x4 cell-owner kernel."""
+    luts = lp.LutSet(lp.load_lut_dict(os.path.join(LUTS, "lerf-g")), device=dev)
+    imgs = natural(8, 1356, 2040, 3000)
+    feat, codes = lp.LerfSR(luts, 4).stages(imgs)
+    for sc, force in ((4, 0), (4, 2), (3.5, 0), (2.5, 0), (1.5, 0)):
+        rs = lp.SteeringGaussianResize2d(support_sz=2, max_sigma=10)
+        rs.set_shape([3, 1356, 2040], scale_factors=[sc, sc])
+        lp.lib().lerf_debug_force_generic(force)
+        out = rs.resize_codes(feat, codes)
+        ms = timeit(lambda: rs.resize_codes(feat, codes, out=out), 10)
+        lp.lib().lerf_debug_force_generic(0)
+        print(json.dumps({"config": "resampler only, LeRF-G x%s, %s kernel" % (sc, "cell-owner" if (sc == 4 and force == 0) else "tile"),
+                          "ms": round(ms, 4), "G_samples_per_s": round(out.numel() / ms / 1e6, 1)}), flush=True)
+
+
 def fixed():
     """Fixed-kernel warps on the cfg-4 in-scale geometry: 1024x1024 uint8 -> 3072x3072 float32."""
     img = natural(1, 1024, 1024, 4000)[0].permute(2, 0, 1).contiguous()
