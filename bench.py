@@ -242,6 +242,8 @@ def run_reference_arm(args, rank):
     rate0, t0, nthreads = cpu_port_rate(64, 3000)
     budget = 150.0 / max(1, args.steps + args.warmup)
     rows = int(max(32, min(H, 64 * budget / t0)))
+    if args.sample_rows > 0:
+        rows = int(min(H, args.sample_rows))
     from oracle import lerf_oracle as orc
     luts = orc.load_luts(LUT_DIR, linear=False)
     img = natural_frame_numpy(3000, rows, W)
@@ -283,6 +285,8 @@ def main():
     ap.add_argument("--input", default="natural", choices=["natural", "uniform"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sample-rows", type=int, default=0,
+                    help="reference arm: rows of the frame band timed per step (0 = sized so the run ends in ~2.5 minutes)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3  # timing rule: W >= 3
