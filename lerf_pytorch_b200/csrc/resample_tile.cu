@@ -17,6 +17,7 @@
 // coefficients are decoded once into shared memory (the float64 kernel decodes them once per output sample and tap).
 #include <math.h>
 
+#include <mutex>
 #include <type_traits>
 
 #include "resample_int.cuh"
@@ -424,6 +425,8 @@ static bool g_warp_records = true;  // testing hook (lerf_debug_warp_records): f
 // (the default pool hands it back to the driver at every synchronisation: 6 ms per 100 MB call, measured).
 static cudaMemPool_t scratch_pool() {
   static cudaMemPool_t pools[64] = {};
+  static std::mutex mu;  // lerf_warp may be called from several host threads (one per stream)
+  std::lock_guard<std::mutex> lock(mu);
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   if (!pools[dev]) {
