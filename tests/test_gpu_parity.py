@@ -3,6 +3,8 @@
 Tolerances are BASELINE.json's: LUT indices / stage outputs bit-exact; fp32 outputs within 1e-4 max-abs of
 the float64 reference; uint8 outputs within 1 LSB; PSNR within 0.01 dB.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -651,6 +653,18 @@ def test_run_host_equals_device_path(lp, luts, hw, scale):
         host_out.zero_()
         sr.run_host(host_in, host_out)
         assert torch.equal(host_out, want)
+
+
+def test_randomised_parity_sweep(lp):
+    """scripts/fuzz_parity.py: random sizes (1..96 x 1..129), integer / near-integer / anisotropic / extreme scales, both
+    models, all formats, random row bands, against the oracle.  30 cases here; 80 were run for profiles/r1e_fuzz_parity_tail.log."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_parity.py"), "30", "777"], capture_output=True,
+                         text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert "all 30 cases within the parity bars" in out.stdout
 
 
 def test_extreme_hypers_no_nan(lp):
