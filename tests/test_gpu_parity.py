@@ -667,6 +667,18 @@ def test_randomised_parity_sweep(lp):
     assert "all 30 cases within the parity bars" in out.stdout
 
 
+def test_randomised_warp_sweep(lp):
+    """scripts/fuzz_warp.py: random sizes and homographies (rotation, anisotropic scale 1..10, shear, perspective, canvases that
+    cut the image), both models: mask identical, fp32 <= 1e-4 and uint8 <= 1 LSB inside the mask."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_warp.py"), "20", "99"], capture_output=True,
+                         text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert "all 20 cases within the parity bars" in out.stdout
+
+
 def test_extreme_hypers_no_nan(lp):
     """All-taps-underflow hazard: sigma = max everywhere, rho = +-1, far taps -> weights ~ 2^-288."""
     H, W = 12, 14
