@@ -410,6 +410,13 @@ def main():
         except Exception:
             pass
 
+    lfile = os.path.join(ROOT, "profiles", "limiters.json")  # what bounds the kernel instead of HBM, from the same ncu capture
+    if os.path.exists(lfile):
+        try:
+            roofline["limiter"] = json.load(open(lfile)).get(top)
+        except Exception:
+            pass
+
     # end to end through the public host API: pinned uint8 frames in, pinned uint8 HWC frames out, copies inside
     e2e = None
     try:
