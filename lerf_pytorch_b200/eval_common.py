@@ -44,6 +44,9 @@ def build_parser(description, default_test_dir):
     p.add_argument('--device', type=str, default='cuda:0')
     p.add_argument('--no-save', dest='save', action='store_false', default=True,
                    help='skip writing PNG / npy results (metrics only)')
+    p.add_argument('--gpu-metrics', dest='gpu_metrics', action='store_true', default=False,
+                   help='compute PSNR-Y / SSIM / mPSNR on the device (metrics_gpu.py); with --no-save the result image never '
+                        'leaves the GPU')
     p.add_argument('--io-threads', dest='io_threads', type=int, default=4,
                    help='host threads that decode the next images and encode / score finished ones while the GPU works '
                         '(SURVEY.md 8f item 2); 0 = everything inline like the reference')

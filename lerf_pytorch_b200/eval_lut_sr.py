@@ -63,9 +63,15 @@ class Evaluator(object):
     def _worker(self, io, fname, img_lr, img_gt, scale_h, scale_w, result_path):
         opt, torch = self.opt, self.torch
         sr = self.engine(scale_h, scale_w)
+        gpu_score = None
         with torch.cuda.device(self.device):
             d_in = torch.from_numpy(np.ascontiguousarray(img_lr.astype(np.uint8))).to(self.device)
-            img_out = sr(d_in, out_format="u8_hwc").cpu().numpy()           # :541-665 incl. the uint8 epilogue
+            d_out = sr(d_in, out_format="u8_hwc")                            # :541-665 incl. the uint8 epilogue
+            if getattr(opt, "gpu_metrics", False):
+                from . import metrics_gpu
+                gpu_score = metrics_gpu.psnr_y_ssim(torch.from_numpy(np.ascontiguousarray(img_gt)).to(self.device), d_out,
+                                                    scale_h, scale_w)
+            img_out = d_out.cpu().numpy() if (opt.save or gpu_score is None) else None
             if opt.save:
                 feat, codes = sr.stages(d_in)
                 feat = feat.cpu().numpy()
@@ -76,6 +82,8 @@ class Evaluator(object):
             io.submit(_save_png, np.ascontiguousarray(feat.transpose((1, 2, 0))), os.path.join(result_path, "{}_lr.png".format(stem)))
             io.submit(_save_png, img_gt, os.path.join(result_path, "{}_gt.png".format(stem)))
             io.submit(np.save, os.path.join(result_path, "{}_{}_hyper.npy".format(fname.split("_")[-1][:-4], opt.lutName)), img_hyper)
+        if gpu_score is not None:
+            return io.submit(lambda: gpu_score)
         return io.submit(metrics.psnr_y_ssim, img_gt, img_out, scale_h, scale_w)
 
 

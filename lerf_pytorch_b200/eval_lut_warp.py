@@ -53,6 +53,12 @@ class Evaluator(object):
         with torch.cuda.device(self.device):
             d_in = torch.from_numpy(np.ascontiguousarray(img_lr.astype(np.uint8))).to(self.device)
             out, mask = self.warp(d_in, matrix, img_gt.shape[:2], out_format="u8_hwc", with_mask=True)
+            if getattr(opt, "gpu_metrics", False) and not opt.save:  # mPSNR on the device: nothing is copied back
+                from . import metrics_gpu
+                d_gt = torch.from_numpy(np.ascontiguousarray(img_gt)).to(self.device)
+                valid3 = mask.to(torch.bool).unsqueeze(-1).expand_as(d_gt)
+                score = [metrics_gpu.mpsnr(out, d_gt, valid3)]
+                return io.submit(lambda: score)
             img_out = out.cpu().numpy()
             valid = mask.cpu().numpy().astype(bool)                        # mask_output == 255 (:229)
             feat = None

@@ -37,3 +37,14 @@ def test_eval_lut_warp_adapter_reproduces_published_table(model, tmp_path):
         argv.append("--linear")
     lines, _ = eval_lut_warp.main(argv)
     assert lines[1].split("\t") == ["Set5".ljust(15, " ")] + WARP_PINS[model]
+
+
+def test_adapters_with_gpu_metrics_print_the_same_tables(tmp_path):
+    """--gpu-metrics: PSNR-Y / SSIM / mPSNR computed on the device (metrics_gpu.py); the printed tables do not change."""
+    from lerf_pytorch_b200 import eval_lut_sr, eval_lut_warp
+    lines, _ = eval_lut_sr.main(["-e", lut_dir("lerf-g"), "--testDir", os.path.join(DATA, "rrBenchmark"), "--resultRoot",
+                                 str(tmp_path), "--no-save", "--gpu-metrics"])
+    assert lines[1].split("\t") == ["Set5".ljust(15, " ")] + SR_PINS["lerf-g"]
+    lines, _ = eval_lut_warp.main(["-e", lut_dir("lerf-g"), "--testDir", os.path.join(DATA, "WarpBenchmark"), "--resultRoot",
+                                   str(tmp_path), "--no-save", "--gpu-metrics"])
+    assert lines[1].split("\t") == ["Set5".ljust(15, " ")] + WARP_PINS["lerf-g"]

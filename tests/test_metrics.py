@@ -39,3 +39,18 @@ def test_adapter_options_and_table_format():
     assert lines[1] == "Set5           \t35.50/0.9250\t30.12/0.8500"
     wl = eval_lut_warp.format_table(["Set5"], ["isc", "osc"], {("Set5", "isc"): [[33.806]], ("Set5", "osc"): [[27.894]]})
     assert wl == ["Scale          \tisc\t\tosc\t", "Set5           \t33.81\t27.89"]
+
+
+def test_gpu_metrics_module_equals_the_host_restatement_on_cpu_tensors():
+    """metrics_gpu.py (torch ops; runs on any device) against metrics.py on the same inputs."""
+    import torch
+    from lerf_pytorch_b200 import metrics, metrics_gpu
+    rng = np.random.default_rng(3)
+    gt = rng.integers(0, 256, (75, 62, 3)).astype(np.uint8)
+    out = np.clip(gt.astype(int) + rng.integers(-12, 13, gt.shape), 0, 255).astype(np.uint8)
+    for sc in (2, 4):
+        a = metrics.psnr_y_ssim(gt, out[:-3, :-1], sc, sc)
+        b = metrics_gpu.psnr_y_ssim(torch.from_numpy(gt), torch.from_numpy(np.ascontiguousarray(out[:-3, :-1])), sc, sc)
+        assert abs(float(a[0]) - b[0]) < 1e-4 and abs(float(a[1]) - b[1]) < 1e-9
+    m = rng.random(gt.shape) < 0.6
+    assert abs(metrics.mpsnr(out, gt, m) - metrics_gpu.mpsnr(torch.from_numpy(out), torch.from_numpy(gt), torch.from_numpy(m))) < 1e-4
