@@ -104,6 +104,9 @@ void sr_pipeline_config(int enabled, int minb, int group_planes);
 int resize_sr_int_gauss(const lerf_sr_plan_impl* P, const uint8_t* feat, const uint8_t* codes, int planes, int channels,
                         float max_sigma, int oy0, int oy1, void* out, int fmt, cudaStream_t st);
 
+int resize_sr_int_linear(const lerf_sr_plan_impl* P, const uint8_t* feat, const uint8_t* codes, int planes, int channels,
+                         float max_sigma, int oy0, int oy1, void* out, int fmt, cudaStream_t st);
+
 void resize_int_config(int variant);
 
 // resample_tile.cu: fast paths for uint8 code inputs; return -1 when they do not apply

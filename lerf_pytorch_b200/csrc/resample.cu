@@ -421,6 +421,10 @@ int lerf_resize_sr(int kind, const lerf_sr_plan_t* plan, const uint8_t* feat, co
       if (rc != -1) return rc;
     }
   }
+  if (kind == LERF_KIND_LINEAR && P->int_scale && g_force_generic == 0) {  // periodic geometry, LeRF-L (resample_int.cu)
+    rc = resize_sr_int_linear(P, feat, codes, planes, channels, max_sigma, oy0, oy1, out, out_format, (cudaStream_t)stream);
+    if (rc != -1) return rc;
+  }
   if (g_force_generic != 1) {  // any scale >= 1: tile kernel (resample_tile.cu); the float64 kernels below are the parity path
     rc = resize_sr_tile(kind, P, feat, codes, planes, channels, max_sigma, oy0, oy1, out, out_format, (cudaStream_t)stream);
     if (rc != -1) return rc;

@@ -86,3 +86,163 @@ int resize_sr_int_gauss(const lerf_sr_plan_impl* P, const uint8_t* feat, const u
 void resize_int_config(int variant) { g_variant = variant; }
 
 }  // namespace lerf
+
+// ---------------------------------------------------------------------------------------------------------------
+// Integer-scale cell-owner kernel for the amplified-linear kind (LeRF-L at x2, x3, x4, x8: the scales of the published
+// LeRF-L table, scripts.sh:36-38).  Replaces AmplifiedLinearResize2dNumpy.resize (resize_right2d_numpy.py:243-282) where
+// the geometry is periodic.  One thread = one cell (the S x S outputs sharing their 2x2 taps); the four taps' alpha
+// values are read once; weights are (1 - alpha |dr|)(1 - alpha |dc|) in float64 like the reference (:233-241) with the
+// phase distances as kernel-parameter constants, then fp32 normalisation around v0 with exact integer differences --
+// the arithmetic of the tile kernel's linear branch (resample_tile.cu), which stays the path for other scales and for
+// max_sigma > 1 (the max(., 0) clamp) or distances outside [-1, 1].
+// ---------------------------------------------------------------------------------------------------------------
+namespace lerf {
+namespace {
+
+template <int S>
+struct LinGeom {
+  double adr[S][2], adc[S][2];  // |dr| [row phase][tap b], |dc| [col phase][tap a]
+  int ph_y, ph_x;
+};
+
+struct SmemLin {
+  double al[256];
+  double sA[kCY + 1][kCX + 1];
+  float sV[kCY + 1][kCX + 1];
+};
+
+template <int S, int FMT>
+__global__ void __launch_bounds__(kCX* kCY)
+    resize_sr_int_linear_kernel(const uint8_t* __restrict__ feat, const uint8_t* __restrict__ codes, int H, int W, int oH, int oW,
+                                const __grid_constant__ LinGeom<S> g, float max_sigma, int channels, int ly0, int oy0, int oy1,
+                                void* __restrict__ out) {
+  __shared__ SmemLin sm;
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int p = blockIdx.z;
+  {  // alpha = fl(max_sigma * rho) in float32 like numpy (:249-250), promoted exactly
+    const float h = __fdiv_rn((float)tid, 255.0f);
+    sm.al[tid] = (double)__fmul_rn(max_sigma, __fsub_rn(__fmul_rn(h, 2.0f), 1.0f));
+  }
+  __syncthreads();
+  const int lx0 = blockIdx.x * kCX - 1, lyb = ly0 + blockIdx.y * kCY;
+  const long long plane_sz = (long long)H * W;
+  const uint8_t* fp = feat + (long long)p * plane_sz;
+  const uint8_t* cp = codes + (long long)p * plane_sz;
+  for (int i = tid; i < (kCY + 1) * (kCX + 1); i += kCX * kCY) {
+    const int r = i / (kCX + 1), c = i - r * (kCX + 1);
+    const int sy = lyb + r, sx = lx0 + c;
+    const int cy = min(max(sy, 0), H - 1), cx = min(max(sx, 0), W - 1);  // hypers: 'edge' (:252-254)
+    const long long off = (long long)cy * W + cx;
+    sm.sA[r][c] = sm.al[__ldcg(cp + off)];
+    sm.sV[r][c] = (sy == cy && sx == cx) ? (float)__ldcg(fp + off) : 0.0f;  // image: 'constant' 0 (:268)
+  }
+  __syncthreads();
+  const int lx = lx0 + tx, ly = lyb + ty;
+  if (lx > W - 1 || ly > H - 1) return;
+  double al[4];
+  float dv[4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {  // taps t = a*2+b: row ly+b, column lx+a (patch order of the reference, :95-98)
+      al[a * 2 + b] = sm.sA[ty + b][tx + a];
+      dv[a * 2 + b] = sm.sV[ty + b][tx + a];
+    }
+  const float v0 = dv[0];
+  dv[1] -= v0; dv[2] -= v0; dv[3] -= v0;  // exact: integers in [-255, 255]
+  const int oyb = S * ly + g.ph_y, oxb = S * lx + g.ph_x;
+  const int pc_ = p % channels;
+  long long rowp = ((long long)p * oH + oyb) * oW;
+  long long rowh = ((long long)(p / channels) * oH + oyb) * oW;
+  const bool full = oxb >= 0 && oxb + S <= oW;
+#pragma unroll
+  for (int mr = 0; mr < S; ++mr, rowp += oW, rowh += oW) {
+    const int oy = oyb + mr;
+    if (oy < oy0 || oy >= oy1) continue;
+    double lr[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) lr[t] = fma(-al[t], g.adr[mr][t & 1], 1.0);
+    float res[S];
+#pragma unroll
+    for (int mc = 0; mc < S; ++mc) {
+      float w[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) w[t] = (float)(lr[t] * fma(-al[t], g.adc[mc][t >> 1], 1.0));
+      const float den = (w[0] + w[1]) + (w[2] + w[3]);
+      const float num = fmaf(w[1], dv[1], fmaf(w[2], dv[2], w[3] * dv[3]));
+      float r;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
+      float qn = num * r;
+      qn = fmaf(fmaf(-den, qn, num), r, qn);
+      res[mc] = v0 + qn;
+    }
+    if (FMT == LERF_OUT_F32 && full && (S % 2 == 0)) {  // same vector stores as the Gaussian kernel (resample_int.cuh)
+      float* o = (float*)out + rowp + oxb;
+      if (S == 8) {
+        __stcg(reinterpret_cast<float4*>(o), make_float4(res[0], res[1], res[2], res[3]));
+        __stcg(reinterpret_cast<float4*>(o + 4), make_float4(res[4 % S], res[5 % S], res[6 % S], res[7 % S]));
+      } else if (S == 4) {
+        __stcg(reinterpret_cast<float2*>(o), make_float2(res[0], res[1]));
+        __stcg(reinterpret_cast<float2*>(o + 2), make_float2(res[2 % S], res[3 % S]));
+      } else {
+        __stcg(o, res[0]);
+        __stcg(o + 1, res[1 % S]);
+      }
+    } else {
+#pragma unroll
+      for (int mc = 0; mc < S; ++mc) {
+        const int ox = oxb + mc;
+        if (ox >= 0 && ox < oW) store1<FMT>(out, rowp + ox, (rowh + ox) * channels + pc_, res[mc]);
+      }
+    }
+  }
+}
+
+template <int S>
+int launch_int_linear(const lerf_sr_plan_impl* P, const uint8_t* feat, const uint8_t* codes, int planes, int channels,
+                      float max_sigma, int oy0, int oy1, void* out, int fmt, cudaStream_t st) {
+  LinGeom<S> g;
+  for (int m = 0; m < S; ++m)
+    for (int k = 0; k < 2; ++k) {
+      g.adr[m][k] = fabs(P->ph_dist_y[m][k]);
+      g.adc[m][k] = fabs(P->ph_dist_x[m][k]);
+      // The linear kernel is DISCONTINUOUS at |d| = 1 (weight 1 - alpha inside, 0 outside) and the per-output distances of
+      // a non-dyadic scale wobble by an ulp around the phase value (x3: p = 1.0 +- 2e-16), so a phase that sits on the
+      // window edge must be decided per output sample: that is the tile kernel's job.  (Seen as 30.76 vs 30.72 dB on
+      // the Set5 x3 table before this guard.)
+      if (g.adr[m][k] > 1.0 - 1e-6 || g.adc[m][k] > 1.0 - 1e-6) return -1;
+    }
+  g.ph_y = P->ph_y;
+  g.ph_x = P->ph_x;
+  const int ly0 = P->h_left_y[oy0], ly1 = P->h_left_y[oy1 - 1];
+  dim3 block(kCX * kCY), grid((P->W + 1 + kCX - 1) / kCX, (ly1 - ly0 + 1 + kCY - 1) / kCY, planes);
+#define LERF_GL(F) \
+  resize_sr_int_linear_kernel<S, F><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, max_sigma, channels, ly0, oy0, oy1, out)
+  switch (fmt) {
+    case LERF_OUT_F32: LERF_GL(LERF_OUT_F32); break;
+    case LERF_OUT_U8: LERF_GL(LERF_OUT_U8); break;
+    case LERF_OUT_U8_HWC: LERF_GL(LERF_OUT_U8_HWC); break;
+    default: return fail(LERF_EINVAL, "unknown out_format %d", fmt);
+  }
+#undef LERF_GL
+  LERF_LAUNCHED();
+  return LERF_OK;
+}
+
+}  // namespace
+
+// Called by lerf_resize_sr (kind = linear) when the plan is periodic.  Returns -1 when this path does not apply.
+int resize_sr_int_linear(const lerf_sr_plan_impl* P, const uint8_t* feat, const uint8_t* codes, int planes, int channels,
+                         float max_sigma, int oy0, int oy1, void* out, int fmt, cudaStream_t st) {
+  if (!(max_sigma >= 0.0f) || max_sigma > 1.0f) return -1;  // |alpha| <= 1 keeps both factors >= 0: no clamp needed
+  if (fmt == LERF_OUT_F32 && ((uintptr_t)out & 15)) return -1;
+  switch (P->int_scale) {
+    case 2: return launch_int_linear<2>(P, feat, codes, planes, channels, max_sigma, oy0, oy1, out, fmt, st);
+    case 3: return launch_int_linear<3>(P, feat, codes, planes, channels, max_sigma, oy0, oy1, out, fmt, st);
+    case 4: return launch_int_linear<4>(P, feat, codes, planes, channels, max_sigma, oy0, oy1, out, fmt, st);
+    case 8: return launch_int_linear<8>(P, feat, codes, planes, channels, max_sigma, oy0, oy1, out, fmt, st);
+    default: return -1;
+  }
+}
+
+}  // namespace lerf

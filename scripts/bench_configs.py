@@ -123,6 +123,22 @@ def tile():
                           "ms": round(ms, 4), "G_samples_per_s": round(out.numel() / ms / 1e6, 1)}), flush=True)
 
 
+def lin():
+    """LeRF-L at x4 on 8 frames 2040x1356, resampler only: cell-owner kernel vs tile kernel."""
+    luts = lp.LutSet(lp.load_lut_dict(os.path.join(LUTS, "lerf-l"), linear=True), linear=True, device=dev)
+    imgs = natural(8, 1356, 2040, 3000)
+    feat, codes = lp.LerfSR(luts, 4).stages(imgs)
+    for force in (0, 2):
+        rs = lp.AmplifiedLinearResize2d()
+        rs.set_shape([3, 1356, 2040], scale_factors=[4, 4])
+        lp.lib().lerf_debug_force_generic(force)
+        out = rs.resize_codes(feat, codes)
+        ms = timeit(lambda: rs.resize_codes(feat, codes, out=out), 10)
+        lp.lib().lerf_debug_force_generic(0)
+        print(json.dumps({"config": "resampler only, LeRF-L x4, %s kernel" % ("cell-owner" if force == 0 else "tile"),
+                          "ms": round(ms, 4), "G_samples_per_s": round(out.numel() / ms / 1e6, 1)}), flush=True)
+
+
 def fixed():
     """Fixed-kernel warps on the cfg-4 in-scale geometry: 1024x1024 uint8 -> 3072x3072 float32."""
     img = natural(1, 1024, 1024, 4000)[0].permute(2, 0, 1).contiguous()

@@ -679,6 +679,36 @@ def test_randomised_warp_sweep(lp):
     assert "all 20 cases within the parity bars" in out.stdout
 
 
+@pytest.mark.parametrize("S", [2, 3, 4, 8])
+def test_linear_int_scale_kernel_vs_tile_kernel_and_oracle(lp, orc, luts, S):
+    """LeRF-L at the integer scales of the published table: cell-owner kernel (resample_int.cu), tile kernel (force_generic 2)
+    and float64 kernel (1) against the oracle; formats and row bands."""
+    ld, ls = luts["l"]
+    img = uniform_image(950 + S, 57, 75)
+    sr = lp.LerfSR(ls, S)
+    dimg = _cuda(img)
+    ref, _, _ = orc.lerf_sr(img, ld, S, S, linear=True)
+    outs = {}
+    try:
+        for level in (0, 2, 1):
+            lp.lib().lerf_debug_force_generic(level)
+            outs[level] = {f: sr(dimg, out_format=f).cpu().numpy() for f in ("f32", "u8", "u8_hwc")}
+            err = _maxabs(outs[level]["f32"], ref)
+            print("LeRF-L x%d %s kernel: max-abs err %.3g" % (S, {0: "cell-owner", 2: "tile", 1: "float64"}[level], err))
+            assert err <= FP32_TOL
+            assert np.max(np.abs(outs[level]["u8_hwc"].astype(int) - orc.to_uint8_hwc(ref).astype(int))) <= 1
+            assert np.array_equal(np.transpose(outs[level]["u8"], (1, 2, 0)), outs[level]["u8_hwc"])
+        lp.lib().lerf_debug_force_generic(0)
+        full = torch.from_numpy(outs[0]["f32"]).cuda()
+        band = torch.zeros_like(full)
+        oH = full.shape[-2]
+        for r0, r1 in ((0, oH // 3), (oH // 3, oH // 2 + 1), (oH // 2 + 1, oH)):
+            sr(dimg, out_format="f32", rows=(r0, r1), out=band.unsqueeze(0))
+        assert torch.equal(band, full)
+    finally:
+        lp.lib().lerf_debug_force_generic(0)
+
+
 def test_extreme_hypers_no_nan(lp):
     """All-taps-underflow hazard: sigma = max everywhere, rho = +-1, far taps -> weights ~ 2^-288."""
     H, W = 12, 14
