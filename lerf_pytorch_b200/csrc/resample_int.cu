@@ -102,6 +102,10 @@ namespace {
 template <int S>
 struct LinGeom {
   double adr[S][2], adc[S][2];  // |dr| [row phase][tap b], |dc| [col phase][tap a]
+  // A phase that sits ON the window edge (|d| = 1 up to rounding; x3 has one): the linear kernel is discontinuous there
+  // (weight 1 - alpha inside, 0 outside) and the per-output distances wobble by an ulp around the phase value, so such a
+  // tap is decided per output sample from the plan's float64 distance tables, exactly like the reference.
+  unsigned char edge_r[S][2], edge_c[S][2];
   int ph_y, ph_x;
 };
 
@@ -111,10 +115,12 @@ struct SmemLin {
   float sV[kCY + 1][kCX + 1];
 };
 
-template <int S, int FMT>
+// EDGE: some phase sits on the window edge (x3); the lean instantiation (x2, x4, x8) carries none of that logic.
+template <int S, int FMT, bool EDGE>
 __global__ void __launch_bounds__(kCX* kCY)
     resize_sr_int_linear_kernel(const uint8_t* __restrict__ feat, const uint8_t* __restrict__ codes, int H, int W, int oH, int oW,
-                                const __grid_constant__ LinGeom<S> g, float max_sigma, int channels, int ly0, int oy0, int oy1,
+                                const __grid_constant__ LinGeom<S> g, const double* __restrict__ dist_y,
+                                const double* __restrict__ dist_x, float max_sigma, int channels, int ly0, int oy0, int oy1,
                                 void* __restrict__ out) {
   __shared__ SmemLin sm;
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
@@ -155,19 +161,46 @@ __global__ void __launch_bounds__(kCX* kCY)
   long long rowp = ((long long)p * oH + oyb) * oW;
   long long rowh = ((long long)(p / channels) * oH + oyb) * oW;
   const bool full = oxb >= 0 && oxb + S <= oW;
+  // column factors of edge phases, from the exact per-output distances (|d| and the [|d| <= 1] window)
+  double edc[S][2];
+  float evc[S][2];
+#pragma unroll
+  for (int mc = 0; mc < S; ++mc)
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      edc[mc][a] = g.adc[mc][a];
+      evc[mc][a] = 1.0f;
+      if (EDGE && g.edge_c[mc][a]) {
+        const int ox = min(max(oxb + mc, 0), oW - 1);
+        edc[mc][a] = fabs(__ldg(dist_x + 2 * ox + a));
+        evc[mc][a] = edc[mc][a] <= 1.0 ? 1.0f : 0.0f;
+      }
+    }
 #pragma unroll
   for (int mr = 0; mr < S; ++mr, rowp += oW, rowh += oW) {
     const int oy = oyb + mr;
     if (oy < oy0 || oy >= oy1) continue;
     double lr[4];
+    float vr[2] = {1.0f, 1.0f};
 #pragma unroll
-    for (int t = 0; t < 4; ++t) lr[t] = fma(-al[t], g.adr[mr][t & 1], 1.0);
+    for (int b = 0; b < 2; ++b) {
+      double d = g.adr[mr][b];
+      if (EDGE && g.edge_r[mr][b]) {
+        d = fabs(__ldg(dist_y + 2 * oy + b));
+        vr[b] = d <= 1.0 ? 1.0f : 0.0f;
+      }
+      lr[b] = fma(-al[b], d, 1.0);
+      lr[2 + b] = fma(-al[2 + b], d, 1.0);
+    }
     float res[S];
 #pragma unroll
     for (int mc = 0; mc < S; ++mc) {
       float w[4];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) w[t] = (float)(lr[t] * fma(-al[t], g.adc[mc][t >> 1], 1.0));
+      for (int t = 0; t < 4; ++t) {
+        w[t] = (float)(lr[t] * fma(-al[t], edc[mc][t >> 1], 1.0));
+        if (EDGE && (g.edge_r[mr][t & 1] || g.edge_c[mc][t >> 1])) w[t] *= vr[t & 1] * evc[mc][t >> 1];
+      }
       const float den = (w[0] + w[1]) + (w[2] + w[3]);
       const float num = fmaf(w[1], dv[1], fmaf(w[2], dv[2], w[3] * dv[3]));
       float r;
@@ -206,18 +239,26 @@ int launch_int_linear(const lerf_sr_plan_impl* P, const uint8_t* feat, const uin
     for (int k = 0; k < 2; ++k) {
       g.adr[m][k] = fabs(P->ph_dist_y[m][k]);
       g.adc[m][k] = fabs(P->ph_dist_x[m][k]);
-      // The linear kernel is DISCONTINUOUS at |d| = 1 (weight 1 - alpha inside, 0 outside) and the per-output distances of
-      // a non-dyadic scale wobble by an ulp around the phase value (x3: p = 1.0 +- 2e-16), so a phase that sits on the
-      // window edge must be decided per output sample: that is the tile kernel's job.  (Seen as 30.76 vs 30.72 dB on
-      // the Set5 x3 table before this guard.)
-      if (g.adr[m][k] > 1.0 - 1e-6 || g.adc[m][k] > 1.0 - 1e-6) return -1;
+      if (g.adr[m][k] > 1.0 + 1e-6 || g.adc[m][k] > 1.0 + 1e-6) return -1;  // outside the window for good: tile kernel
+      // on the window edge: decided per output sample in the kernel (taking the phase constant moved the Set5 x3 entry
+      // of the published LeRF-L table from 30.72 to 30.76 dB)
+      g.edge_r[m][k] = g.adr[m][k] > 1.0 - 1e-6;
+      g.edge_c[m][k] = g.adc[m][k] > 1.0 - 1e-6;
     }
   g.ph_y = P->ph_y;
   g.ph_x = P->ph_x;
   const int ly0 = P->h_left_y[oy0], ly1 = P->h_left_y[oy1 - 1];
   dim3 block(kCX * kCY), grid((P->W + 1 + kCX - 1) / kCX, (ly1 - ly0 + 1 + kCY - 1) / kCY, planes);
-#define LERF_GL(F) \
-  resize_sr_int_linear_kernel<S, F><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, max_sigma, channels, ly0, oy0, oy1, out)
+  bool edge = false;
+  for (int m = 0; m < S; ++m)
+    for (int k = 0; k < 2; ++k) edge = edge || g.edge_r[m][k] || g.edge_c[m][k];
+#define LERF_GL(F)                                                                                                                  \
+  if (edge)                                                                                                                         \
+    resize_sr_int_linear_kernel<S, F, true><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, P->dist_y, P->dist_x,  \
+                                                                    max_sigma, channels, ly0, oy0, oy1, out);                        \
+  else                                                                                                                              \
+    resize_sr_int_linear_kernel<S, F, false><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, P->dist_y, P->dist_x, \
+                                                                     max_sigma, channels, ly0, oy0, oy1, out)
   switch (fmt) {
     case LERF_OUT_F32: LERF_GL(LERF_OUT_F32); break;
     case LERF_OUT_U8: LERF_GL(LERF_OUT_U8); break;

@@ -128,14 +128,14 @@ def lin():
     luts = lp.LutSet(lp.load_lut_dict(os.path.join(LUTS, "lerf-l"), linear=True), linear=True, device=dev)
     imgs = natural(8, 1356, 2040, 3000)
     feat, codes = lp.LerfSR(luts, 4).stages(imgs)
-    for force in (0, 2):
+    for sc, force in ((4, 0), (4, 2), (3, 0), (3, 2)):
         rs = lp.AmplifiedLinearResize2d()
-        rs.set_shape([3, 1356, 2040], scale_factors=[4, 4])
+        rs.set_shape([3, 1356, 2040], scale_factors=[sc, sc])
         lp.lib().lerf_debug_force_generic(force)
         out = rs.resize_codes(feat, codes)
         ms = timeit(lambda: rs.resize_codes(feat, codes, out=out), 10)
         lp.lib().lerf_debug_force_generic(0)
-        print(json.dumps({"config": "resampler only, LeRF-L x4, %s kernel" % ("cell-owner" if force == 0 else "tile"),
+        print(json.dumps({"config": "resampler only, LeRF-L x%d, %s kernel" % (sc, "cell-owner" if force == 0 else "tile"),
                           "ms": round(ms, 4), "G_samples_per_s": round(out.numel() / ms / 1e6, 1)}), flush=True)
 
 
