@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "liblerf_b200.so")
-SOURCES = ["lut.cu", "lut_cell.cu", "resample.cu", "resample_int.cu", "resample_tile.cu", "warp_fixed.cu", "fused.cu", "pipeline.cu"]
+SOURCES = ["lut.cu", "lut_cell.cu", "lut_pw.cu", "resample.cu", "resample_int.cu", "resample_tile.cu", "warp_fixed.cu", "fused.cu", "pipeline.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
@@ -22,7 +22,7 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(HERE, "csrc", s) for s in SOURCES + ["common.cuh", "lut_cell.cuh", "lut_rm.cuh", "lut_cell_body.cuh", "lut_mix.cuh", "lut_mt.cuh", "resample_int.cuh"]] + [os.path.join(ROOT, "include", "lerf_b200.h")]
+    deps = [os.path.join(HERE, "csrc", s) for s in SOURCES + ["common.cuh", "lut_cell.cuh", "lut_rm.cuh", "lut_cell_body.cuh", "lut_mix.cuh", "lut_mt.cuh", "lut_pw.cuh", "resample_int.cuh"]] + [os.path.join(ROOT, "include", "lerf_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

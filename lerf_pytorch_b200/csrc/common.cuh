@@ -64,6 +64,11 @@ struct lerf_luts_impl {
   // max-tap block copies of the oC = 3 stage-2 tables (lut_mt.cuh): 65536 cells x 4 blocks x 32 B each
   void* mt_block;
   const uint8_t* mt2[6];
+  // paired-window copies (lut_pw.cuh): 6 window families per stage, 64 planes x 65536 blocks of 16 B (oC 1) / 32 B (oC 3)
+  void* pw_block;
+  size_t pw_block_bytes;
+  const uint8_t* pw1[6];
+  const uint8_t* pw2[6];
 };
 
 struct lerf_sr_plan_impl {
@@ -88,6 +93,11 @@ struct lerf_sr_plan_impl {
 int build_cell_tables(lerf_luts_impl* L, const int8_t* const host_tables[9]);
 int launch_stage_cell(const lerf_luts_impl* L, int stage, const uint8_t* in, const InAddr& ia, int planes, int H, int W,
                       int y0, int y1, uint8_t* out, int variant, cudaStream_t st);
+
+// lut_pw.cu
+int build_pw_tables(lerf_luts_impl* L);
+int launch_stage_pw(const lerf_luts_impl* L, int stage, const uint8_t* in, const InAddr& ia, int planes, int H, int W,
+                    int y0, int y1, uint8_t* out, int variant, cudaStream_t st);
 
 int launch_stage2_mix(const lerf_luts_impl* L, const uint8_t* feat, int planes, int H, int W, int y0, int y1, uint8_t* out,
                       int variant, cudaStream_t st);

@@ -150,7 +150,9 @@ int lerf_luts_create(const int8_t* const host_tables[9], int oC2, int device, le
   for (int i = 0; i < 6; ++i) L->s2[i] = (uint8_t*)L->block + 3 * s1_bytes + i * s2_bytes;
   for (int i = 0; i < 3; ++i) L->cell_hash[i] = g_cell_hash[i];
   int rc = build_cell_tables(L, host_tables);
+  if (!rc) rc = build_pw_tables(L);
   if (rc) {
+    cudaFree(L->pw_block);
     cudaFree(L->mt_block);
     cudaFree(L->cell_block);
     cudaFree(L->block);
@@ -172,6 +174,7 @@ void lerf_luts_destroy(lerf_luts_t* luts) {
   cudaFree(L->block);
   cudaFree(L->cell_block);
   cudaFree(L->mt_block);
+  cudaFree(L->pw_block);
   delete L;
 }
 
@@ -229,6 +232,8 @@ int lerf_lut_stage1(const lerf_luts_t* luts, const uint8_t* in, int planes, int 
   for (int i = 0; i < 3; ++i) t.t[i] = L->s1[i];
   for (int i = 3; i < 6; ++i) t.t[i] = nullptr;
   InAddr ia{in_channels, in_batch_stride, in_chan_stride, in_row_stride, in_pix_stride};
+  if (g_lut_variant[0] >= 80)  // paired-window tables (lut_pw.cu)
+    return launch_stage_pw(L, 1, in, ia, planes, H, W, y0, y1, feat, g_lut_variant[0] - 80, (cudaStream_t)stream);
   if (g_lut_variant[0] == 0 || g_lut_variant[0] >= 20)  // production: cell-packed tables (lut_cell.cu)
     return launch_stage_cell(L, 1, in, ia, planes, H, W, y0, y1, feat, g_lut_variant[0] >= 20 ? g_lut_variant[0] - 20 : 0,
                              (cudaStream_t)stream);
@@ -262,7 +267,9 @@ int lerf_lut_stage2(const lerf_luts_t* luts, const uint8_t* feat, int planes, in
   rm::StageTables t;
   for (int i = 0; i < 6; ++i) t.t[i] = L->s2[i];
   InAddr ia{1, (long long)H * W, 0, W, 1};
-  if ((g_lut_variant[1] >= 60 || g_lut_variant[1] == 0) && L->oC2 == 3)  // production: max-tap block tables (lut_mt.cuh)
+  if (g_lut_variant[1] >= 80 || (g_lut_variant[1] == 0 && L->oC2 == 3))  // production (LeRF-G): paired-window tables (lut_pw.cu)
+    return launch_stage_pw(L, 2, feat, ia, planes, H, W, y0, y1, codes, g_lut_variant[1] >= 80 ? g_lut_variant[1] - 80 : 0, (cudaStream_t)stream);
+  if (g_lut_variant[1] >= 60 && L->oC2 == 3)  // max-tap block tables (lut_mt.cuh), production until r2a
     return launch_stage2_mt(L, feat, planes, H, W, y0, y1, codes, g_lut_variant[1] >= 60 ? g_lut_variant[1] - 60 : 10,  // 10: single-word taps, 5 blocks/SM
                             (cudaStream_t)stream);
   if (g_lut_variant[1] >= 40 && L->oC2 == 3)  // table-format mix (lut_mix.cuh)

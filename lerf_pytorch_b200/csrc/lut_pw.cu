@@ -1,0 +1,309 @@
+// Rotation-ensembled LUT stages on paired-window tables (lut_pw.cuh): table build (repack kernel) and the stage kernel.
+// Reference being replaced (ddlee-cn/LeRF-PyTorch): stage-1 / stage-2 loops resample/eval_lut_sr.py:541-628
+// (= eval_lut_warp.py:104-191) over FourSimplexInterpFaster (:24-470).
+//
+// Kernel: one CTA = one 32 x 32 pixel tile of one plane, 256 threads, a thread owns the pixels (tx, tq + 8j).  The
+// unit of work is a WINDOW anchored at a pixel: a 2x2 block, a horizontal / vertical 4-segment, a diagonal and an
+// anti-diagonal.  Each window is sorted once and fetches one block per table that holds both orientations, i.e. two
+// of the twelve lookups of the ensemble (four for the 2x2 block, from two tables).  The lookup that belongs to
+// the anchor pixel accumulates in the owner's registers; the one that belongs to the pixel at the far end of the
+// window goes through seven shared-memory exchange arrays, one per (family, far end), each written exactly once per
+// tile pixel -- plain stores, one barrier before the final sum.
+// Windows whose anchor lies in the 3-pixel halo around the tile only feed the far end ("halo anchors": they ride
+// along as a fifth element of each thread's batch of loads).  Pixels outside the image are edge-replicated when the
+// tile is staged, which is exactly what the reference's rotate-then-pad does, so a window that hangs
+// over the border still pairs up.
+// Measured (B200, r2a, 8 frames 2040x1356): stage 2 (LeRF-G) 271 us per frame on natural-like input (max-tap kernel:
+// 345), 337 on uniform input (372); 6.7 sectors per sample cross the L2 -> L1 link instead of 12.
+#include <vector>
+
+#include "common.cuh"
+#include "lut_pw.cuh"
+
+namespace lerf {
+namespace pwk {
+
+constexpr int kT = 32, kHalo = 3, kPitch = 40, kRows = kT + 2 * kHalo;
+
+struct Tables {
+  const uint8_t* t[6];
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// repack: row-major T[17^4][oC] (device) -> paired-window table of family f
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void pw_repack_kernel(const int8_t* __restrict__ T, int oC, int entry_stride, int f, uint8_t* __restrict__ dst) {
+  const uint32_t cellidx = blockIdx.x * blockDim.x + threadIdx.x;  // 65536 cells
+  const uint32_t code = blockIdx.y;                                // 64 codes
+  uint8_t blk[32];
+  if (!pw::fill_block(T, oC, entry_stride, f, cellidx, code, blk)) return;
+  const size_t B = pw::block_bytes(oC);
+  uint4* o = reinterpret_cast<uint4*>(dst + (((size_t)code << 16) | cellidx) * B);
+  const uint4* s = reinterpret_cast<const uint4*>(blk);
+  o[0] = s[0];
+  if (oC == 3) o[1] = s[1];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// packed accumulators: oC = 3 keeps (n0 + n1 * 65536, n2) -- every partial sum of the twelve |N| <= 2048 fits 16 bits
+// ---------------------------------------------------------------------------------------------------------------
+template <int OC>
+struct Pk;
+template <>
+struct Pk<3> {
+  int a, b;
+  __device__ __forceinline__ void zero() { a = b = 0; }
+  __device__ __forceinline__ void add(const Pk& o) { a += o.a; b += o.b; }
+  __device__ __forceinline__ void set(const int* n) { a = n[1] * 65536 + n[0]; b = n[2]; }
+  __device__ __forceinline__ void get(int* n) const {
+    n[0] = (int)(short)(a & 0xFFFF);
+    n[1] = (a - n[0]) >> 16;
+    n[2] = b;
+  }
+};
+template <>
+struct Pk<1> {
+  int a;
+  __device__ __forceinline__ void zero() { a = 0; }
+  __device__ __forceinline__ void add(const Pk& o) { a += o.a; }
+  __device__ __forceinline__ void set(const int* n) { a = n[0]; }
+  __device__ __forceinline__ void get(int* n) const { n[0] = a; }
+};
+
+// LD: 0 = ld.global.nc (allocates in L1), 1 = nc + L1::no_allocate
+template <int OC, int LD>
+__device__ __forceinline__ void fetch(const uint8_t* __restrict__ tab, uint32_t block, uint32_t* q) {
+  if (OC == 3) {
+    const uint8_t* p = tab + (size_t)block * 32;
+    if (LD == 1)
+      asm("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+          : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])
+          : "l"(p));
+    else
+      asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+          : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])
+          : "l"(p));
+  } else {
+    const uint8_t* p = tab + (size_t)block * 16;
+    if (LD == 1)
+      asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]) : "l"(p));
+    else
+      asm("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]) : "l"(p));
+  }
+}
+
+template <int OC>
+__device__ __forceinline__ void blend(const uint32_t* q, const pw::Lookup& L, Pk<OC>& o0, Pk<OC>& o1) {
+  if (OC == 3) {
+    int n[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    pw::blend3(q, L, n);
+    o0.set(n[0]);
+    o1.set(n[1]);
+  } else {
+    int n[2] = {0, 0};
+    pw::blend1(q, L, n);
+    o0.set(&n[0]);
+    o1.set(&n[1]);
+  }
+}
+
+__device__ __forceinline__ bool in_tile(int x, int y) { return (unsigned)x < (unsigned)kT && (unsigned)y < (unsigned)kT; }
+
+__device__ __forceinline__ int rhe_div(int num, int den) {  // round_half_even(num / den), num > 0, den even
+  const int t = num + den / 2;
+  int q = t / den;
+  if (t - q * den == 0 && (q & 1)) --q;
+  return q;
+}
+
+// Window group G (0 = 2x2 block, 1 = CH, 2 = CV, 3 = TD, 4 = TA): tap offsets in tile words, number of halo anchors and
+// their coordinates, destination of the far-end lookup.
+template <int G>
+struct Grp {
+  static constexpr int P = kPitch;
+  static constexpr int o1 = G == 0 ? 1 : (G == 1 ? 1 : (G == 2 ? P : (G == 3 ? P + 1 : P - 1)));
+  static constexpr int o2 = G == 0 ? P : 2 * o1, o3 = G == 0 ? P + 1 : 3 * o1;
+  static constexpr int nhalo = G == 0 ? 65 : (G == 1 || G == 2 ? 96 : 201);
+  static constexpr int ddx = G == 0 ? 1 : (G == 1 ? 3 : (G == 2 ? 0 : (G == 3 ? 3 : -3)));
+  static constexpr int ddy = G == 0 ? 1 : (G == 1 ? 0 : 3);
+  __device__ static __forceinline__ void halo(int i, int& ax, int& ay) {
+    if (G == 0) { ax = i < 33 ? -1 : i - 33; ay = i < 33 ? i - 1 : -1; }              // column -1, then row -1
+    if (G == 1) { ax = -3 + i % 3; ay = i / 3; }                                     // columns -3..-1
+    if (G == 2) { ax = i & 31; ay = -3 + (i >> 5); }                                 // rows -3..-1
+    if (G == 3) { ax = i < 105 ? -3 + i % 35 : -3 + (i - 105) % 3; ay = i < 105 ? -3 + i / 35 : (i - 105) / 3; }
+    if (G == 4) { ax = i < 105 ? i % 35 : 32 + (i - 105) % 3; ay = i < 105 ? -3 + i / 35 : (i - 105) / 3; }
+  }
+};
+
+// One pass of group G over the tile: the thread's four anchors (tx, tq + 8j) plus at most one halo anchor.  All five
+// table loads are issued before the first one is consumed (the kernel lives on load latency: ncu r2a, long_scoreboard).
+// Exchange arrays (each written exactly once per tile pixel, so plain stores and a single barrier before the final
+// sum):  X[0] S0.o1 (+1,+1)   X[1] S1.o0 (+1,0)   X[2] S1.o1 (0,+1)   X[3] CH (+3,0)   X[4] CV (0,+3)   X[5] TD (+3,+3)   X[6] TA (-3,+3)
+template <int OC, int LD, int G>
+__device__ __forceinline__ void group_pass(const Tables& t, const uint32_t* __restrict__ tile, Pk<OC>* __restrict__ X, int tx,
+                                           int tq, int tid, Pk<OC> own[4]) {
+  using Gr = Grp<G>;
+  constexpr int nq = OC == 3 ? 8 : 4;
+  constexpr int kPx = kT * kT;
+  pw::Lookup L[5];
+  uint32_t q[5][nq];
+  int hx = 0, hy = 0;
+  const bool h = tid < Gr::nhalo;
+  if (h) Gr::halo(tid, hx, hy);
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    if (j == 4 && !h) break;
+    const int ax = j < 4 ? tx : hx, ay = j < 4 ? tq + 8 * j : hy;
+    const uint32_t* c = tile + (ay + kHalo) * kPitch + ax + kHalo;
+    L[j] = pw::prepare(c[0], c[Gr::o1], c[Gr::o2], c[Gr::o3]);
+    fetch<OC, LD>(t.t[G == 0 ? 0 : G + 1], L[j].block, q[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    if (j == 4 && !h) break;
+    const int ax = j < 4 ? tx : hx, ay = j < 4 ? tq + 8 * j : hy;
+    Pk<OC> f, r;
+    blend<OC>(q[j], L[j], f, r);
+    if (j < 4) own[j].add(f);
+    const int dx = ax + Gr::ddx, dy = ay + Gr::ddy;
+    if (in_tile(dx, dy)) X[(G == 0 ? 0 : G + 2) * kPx + dy * kT + dx] = r;
+  }
+  if (G == 0) {  // the second table of the 2x2 block: rotation 1 lands on B (+1,0), rotation 3 on C (0,+1)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      if (j == 4 && !h) break;
+      fetch<OC, LD>(t.t[1], L[j].block, q[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      if (j == 4 && !h) break;
+      const int ax = j < 4 ? tx : hx, ay = j < 4 ? tq + 8 * j : hy;
+      Pk<OC> b0, b1;
+      blend<OC>(q[j], L[j], b0, b1);
+      if (in_tile(ax + 1, ay)) X[1 * kPx + ay * kT + ax + 1] = b0;
+      if (in_tile(ax, ay + 1)) X[2 * kPx + (ay + 1) * kT + ax] = b1;
+    }
+  }
+}
+
+template <int STAGE, int OC, int LD, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+    lut_stage_pw_kernel(Tables t, const uint8_t* __restrict__ in, InAddr ia, int H, int W, int y0, int y1,
+                        uint8_t* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* tile = reinterpret_cast<uint32_t*>(smem_raw);
+  Pk<OC>* X = reinterpret_cast<Pk<OC>*>(smem_raw + kRows * kPitch * 4);
+  const int bx = blockIdx.x * kT, by = y0 + blockIdx.y * kT, p = blockIdx.z;
+  const uint8_t* src = in + (long long)(p / ia.channels) * ia.batch_stride + (long long)(p % ia.channels) * ia.chan_stride;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < kRows * kRows; i += 256) {
+    const int r = i / kRows, c = i - r * kRows;
+    const int gy = min(max(by + r - kHalo, 0), H - 1), gx = min(max(bx + c - kHalo, 0), W - 1);
+    tile[r * kPitch + c] = cell::split_px(__ldcg(src + (long long)gy * ia.row_stride + (long long)gx * ia.pix_stride));
+  }
+  __syncthreads();
+  const int tx = tid & 31, tq = tid >> 5;
+  Pk<OC> own[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) own[j].zero();
+  group_pass<OC, LD, 0>(t, tile, X, tx, tq, tid, own);
+  group_pass<OC, LD, 1>(t, tile, X, tx, tq, tid, own);
+  group_pass<OC, LD, 2>(t, tile, X, tx, tq, tid, own);
+  group_pass<OC, LD, 3>(t, tile, X, tx, tq, tid, own);
+  group_pass<OC, LD, 4>(t, tile, X, tx, tq, tid, own);
+  __syncthreads();
+
+  const int x = bx + tx;
+  if (x >= W) return;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int ty = tq + 8 * j, y = by + ty;
+    if (y >= y1) continue;
+    Pk<OC> s = own[j];
+#pragma unroll
+    for (int a = 0; a < 7; ++a) s.add(X[a * kT * kT + ty * kT + tx]);
+    int n[3];
+    s.get(n);
+#pragma unroll
+    for (int k = 0; k < OC; ++k) {
+      int v;
+      if (STAGE == 1) {
+        v = n[k] <= 0 ? 0 : min(rhe_div(n[k], 48), 255);
+      } else {
+        const int u = n[k] + 127 * 192;
+        v = u <= 0 ? 0 : min(rhe_div(u, 192), 255);
+      }
+      __stcg(out + ((long long)(p * OC + k) * H + y) * W + x, (uint8_t)v);
+    }
+  }
+}
+
+template <int OC>
+constexpr size_t smem_bytes() { return (size_t)kRows * kPitch * 4 + (size_t)7 * kT * kT * sizeof(Pk<OC>); }
+
+}  // namespace pwk
+
+// Builds the paired-window copies of the nine tables: 6 families per stage (stage 1: family f reads table f >> 1).
+int build_pw_tables(lerf_luts_impl* L) {
+  const int oC = L->oC2;
+  const size_t b1 = pw::table_bytes(1), b2 = pw::table_bytes(oC);
+  const size_t total = 6 * b1 + 6 * b2;
+  cudaError_t e = cudaMalloc(&L->pw_block, total);
+  if (e != cudaSuccess) return fail(LERF_ENOMEM, "cudaMalloc(%zu) for the paired-window LUT block failed: %s", total, cudaGetErrorString(e));
+  L->pw_block_bytes = total;
+  dim3 grid(65536 / 256, 64);
+  for (int f = 0; f < 6; ++f) {
+    uint8_t* d1 = (uint8_t*)L->pw_block + f * b1;
+    uint8_t* d2 = (uint8_t*)L->pw_block + 6 * b1 + f * b2;
+    pwk::pw_repack_kernel<<<grid, 256>>>(L->s1[f >> 1], 1, 1, f, d1);
+    // the row-major device copy of an oC = 3 table is padded to 4 bytes per entry
+    pwk::pw_repack_kernel<<<grid, 256>>>((const int8_t*)L->s2[f], oC, oC == 3 ? 4 : 1, f, d2);
+    L->pw1[f] = d1;
+    L->pw2[f] = d2;
+  }
+  e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return fail(LERF_ECUDA, "paired-window LUT repack failed: %s", cudaGetErrorString(e));
+  return LERF_OK;
+}
+
+int launch_stage_pw(const lerf_luts_impl* L, int stage, const uint8_t* in, const InAddr& ia, int planes, int H, int W,
+                    int y0, int y1, uint8_t* out, int variant, cudaStream_t st) {
+  if (!L->pw_block) return fail(LERF_EUNSUPPORTED, "paired-window tables were not built for this LUT set");
+  pwk::Tables t;
+  for (int i = 0; i < 6; ++i) t.t[i] = stage == 1 ? L->pw1[i] : L->pw2[i];
+  dim3 grid((W + pwk::kT - 1) / pwk::kT, (y1 - y0 + pwk::kT - 1) / pwk::kT, planes);
+#define LERF_GO(S, O, LD, B)                                                                                      \
+  {                                                                                                               \
+    static bool attr_set = false; /* per instantiation: > 48 KB of dynamic shared memory needs the opt-in */       \
+    if (!attr_set) {                                                                                              \
+      LERF_CUDA(cudaFuncSetAttribute(pwk::lut_stage_pw_kernel<S, O, LD, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)pwk::smem_bytes<O>()));                                                 \
+      attr_set = true;                                                                                            \
+    }                                                                                                             \
+    pwk::lut_stage_pw_kernel<S, O, LD, B><<<grid, 256, pwk::smem_bytes<O>(), st>>>(t, in, ia, H, W, y0, y1, out);  \
+  }
+  if (stage == 1) {
+    switch (variant) {
+      case 1: LERF_GO(1, 1, 0, 3) break;
+      case 2: LERF_GO(1, 1, 1, 4) break;
+      case 3: LERF_GO(1, 1, 0, 4) break;
+      default: LERF_GO(1, 1, 1, 3)
+    }
+  } else if (L->oC2 == 3) {
+    switch (variant) {
+      case 1: LERF_GO(2, 3, 0, 3) break;
+      case 2: LERF_GO(2, 3, 1, 2) break;
+      default: LERF_GO(2, 3, 1, 3)
+    }
+  } else {
+    switch (variant) {
+      case 1: LERF_GO(2, 1, 0, 3) break;
+      default: LERF_GO(2, 1, 1, 3)
+    }
+  }
+#undef LERF_GO
+  LERF_LAUNCHED();
+  return LERF_OK;
+}
+
+}  // namespace lerf

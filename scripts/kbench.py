@@ -38,7 +38,9 @@ def timeit(fn):
 for kind in os.environ.get("KB_KINDS", "natural,uniform").split(","):
     frames = (bench.natural_frames_gpu if kind == "natural" else bench.uniform_frames_gpu)(B, 3000, dev)
     ref_feat = None
-    s1_variants = ((0, "cell (production)"), (1, "row-major minb3"), (25, "cell minb5"), (26, "cell minb6"))
+    s1_variants = ((0, "cell (production)"), (1, "row-major minb3"), (25, "cell minb5"), (26, "cell minb6"), (80, "pw minb3"), (81, "pw L1 minb3"), (82, "pw minb4"), (83, "pw L1 minb4"))
+    if ONLY == "pw":
+        s1_variants = tuple(x for x in s1_variants if x[0] == 0 or x[0] >= 80)
     for v, name in (s1_variants[:1] if ONLY == "prod" else s1_variants):
         L.lerf_debug_lut_variant(1, v)
         feat = lp.lut_stage1(luts, frames)
@@ -48,7 +50,9 @@ for kind in os.environ.get("KB_KINDS", "natural,uniform").split(","):
         print("%-8s stage1 %-24s %8.1f us/frame" % (kind, name, timeit(lambda: lp.lut_stage1(luts, frames, out=feat))), flush=True)
     L.lerf_debug_lut_variant(1, 0)
     codes = lp.lut_stage2(luts, ref_feat)
-    s2_variants = ((0, "production (max-tap v10)"), (1, "row-major minb4"), (23, "cell-48B minb3")) + tuple((60 + k, "max-tap v%d" % k) for k in range(13)) + ((42, "mix rm+max-tap 8/12"),)
+    s2_variants = ((0, "production (pw minb3)"), (70, "max-tap v10"), (1, "row-major minb4"), (23, "cell-48B minb3")) + tuple((60 + k, "max-tap v%d" % k) for k in range(13)) + ((42, "mix rm+max-tap 8/12"), (80, "pw minb3"), (81, "pw L1 minb3"), (82, "pw minb2"))
+    if ONLY == "pw":
+        s2_variants = tuple(x for x in s2_variants if x[0] in (0, 70) or x[0] >= 80)
     for v, name in (s2_variants[:1] if ONLY == "prod" else s2_variants):
         L.lerf_debug_lut_variant(2, v)
         c2 = lp.lut_stage2(luts, ref_feat)
@@ -78,13 +82,14 @@ for kind in os.environ.get("KB_KINDS", "natural,uniform").split(","):
     for fmt in ("f32", "u8", "u8_hwc"):
         out = rs.resize_codes(ref_feat, codes, out_format=fmt)
         print("%-8s resize %-20s %8.1f us/frame" % (kind, "int-scale " + fmt, timeit(lambda: rs.resize_codes(ref_feat, codes, out_format=fmt, out=out))), flush=True)
-    if ONLY != "prod":
+    if ONLY not in ("prod", "pw"):
         out = rs.resize_codes(ref_feat, codes, out_format="f32")
         for v in (0, 1, 2, 4, 5):
             L.lerf_debug_resize_variant(v)
             print("%-8s resize f32 variant %d           %8.1f us/frame" % (kind, v, timeit(lambda: rs.resize_codes(ref_feat, codes, out_format="f32", out=out))), flush=True)
         L.lerf_debug_resize_variant(0)
-    L.lerf_debug_force_generic(1)
-    out = rs.resize_codes(ref_feat, codes)
-    print("%-8s resize %-20s %8.1f us/frame" % (kind, "generic f32", timeit(lambda: rs.resize_codes(ref_feat, codes, out=out))), flush=True)
-    L.lerf_debug_force_generic(0)
+    if ONLY not in ("prod", "pw"):
+        L.lerf_debug_force_generic(1)
+        out = rs.resize_codes(ref_feat, codes)
+        print("%-8s resize %-20s %8.1f us/frame" % (kind, "generic f32", timeit(lambda: rs.resize_codes(ref_feat, codes, out=out))), flush=True)
+        L.lerf_debug_force_generic(0)

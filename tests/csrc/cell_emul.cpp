@@ -138,3 +138,58 @@ extern "C" int emul_stage2_maxtap1(const int8_t* const* tables, const uint8_t* i
       }
   return 0;
 }
+
+// Paired-window format (lut_pw.cuh): every window is sorted once and one block per table serves both orientations;
+// walked window by window over the whole (edge-replicated) image like lut_stage_pw_kernel does per tile.
+#include "../../lerf_pytorch_b200/csrc/lut_pw.cuh"
+
+extern "C" int emul_stage_pw(int stage, const int8_t* const* tables, int oC, const uint8_t* img, int P, int H, int W,
+                             uint8_t* out) {
+  namespace pw = lerf::pw;
+  static const int dest[6][2][2] = {{{0, 0}, {1, 1}}, {{1, 0}, {0, 1}}, {{0, 0}, {3, 0}},
+                                    {{0, 0}, {0, 3}}, {{0, 0}, {3, 3}}, {{0, 0}, {-3, 3}}};  // [family][orientation](dx, dy)
+  std::vector<int> acc((size_t)P * oC * H * W, 0);
+  for (int p = 0; p < P; ++p)
+    for (int f = 0; f < 6; ++f) {
+      const int8_t* T = tables[stage == 1 ? (f >> 1) : f];
+      for (int ay = -3; ay < H; ++ay)
+        for (int ax = -3; ax < W + 3; ++ax) {
+          uint32_t w[4];
+          for (int k = 0; k < 4; ++k) {
+            int dx, dy;
+            pw::window_tap(f, k, dx, dy);
+            w[k] = split_px(img[((size_t)p * H + clampi(ay + dy, 0, H - 1)) * W + clampi(ax + dx, 0, W - 1)]);
+          }
+          const pw::Lookup L = pw::prepare(w[0], w[1], w[2], w[3]);
+          uint8_t blk[32];
+          if (!pw::fill_block(T, oC, oC, f, L.block & 0xFFFFu, L.block >> 16, blk)) return 1;  // an impossible order code
+          uint32_t q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          memcpy(q, blk, pw::block_bytes(oC));
+          int n[2][3] = {{0, 0, 0}, {0, 0, 0}};
+          if (oC == 3) {
+            pw::blend3(q, L, n);
+          } else {
+            int m[2] = {0, 0};
+            pw::blend1(q, L, m);
+            n[0][0] = m[0];
+            n[1][0] = m[1];
+          }
+          for (int o = 0; o < 2; ++o) {
+            const int x = ax + dest[f][o][0], y = ay + dest[f][o][1];
+            if (x < 0 || x >= W || y < 0 || y >= H) continue;
+            for (int ch = 0; ch < oC; ++ch) acc[(((size_t)p * oC + ch) * H + y) * W + x] += n[o][ch];
+          }
+        }
+    }
+  for (size_t i = 0; i < acc.size(); ++i) {
+    int v;
+    if (stage == 1) {
+      v = acc[i] <= 0 ? 0 : (rhe_div(acc[i], 48) > 255 ? 255 : rhe_div(acc[i], 48));
+    } else {
+      const int t = acc[i] + 127 * 192;
+      v = t <= 0 ? 0 : (rhe_div(t, 192) > 255 ? 255 : rhe_div(t, 192));
+    }
+    out[i] = (uint8_t)v;
+  }
+  return 0;
+}

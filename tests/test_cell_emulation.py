@@ -15,11 +15,12 @@ SRC = os.path.join(HERE, "csrc", "cell_emul.cpp")
 LIB = os.path.join(HERE, "csrc", "libcell_emul.so")
 HDR = os.path.join(os.path.dirname(HERE), "lerf_pytorch_b200", "csrc", "lut_cell.cuh")
 HDR2 = os.path.join(os.path.dirname(HERE), "lerf_pytorch_b200", "csrc", "lut_mt.cuh")
+HDR3 = os.path.join(os.path.dirname(HERE), "lerf_pytorch_b200", "csrc", "lut_pw.cuh")
 
 
 @pytest.fixture(scope="module")
 def emul():
-    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(HDR), os.path.getmtime(HDR2)):
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(SRC), os.path.getmtime(HDR), os.path.getmtime(HDR2), os.path.getmtime(HDR3)):
         gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         env = dict(os.environ)
         env.pop("CC", None)
@@ -81,3 +82,35 @@ def test_maxtap_block_lookup_equals_oracle(emul, kind):
         out[:] = 0
         assert fn(arr, ctypes.c_void_p(f.ctypes.data), 3, f.shape[1], f.shape[2], ctypes.c_void_p(out.ctypes.data)) == 0
         assert np.array_equal(out, codes)
+
+
+@pytest.mark.parametrize("oC,kind", [(3, "shipped"), (1, "shipped"), (3, "random"), (1, "random")])
+def test_paired_window_lookup_equals_oracle(emul, oC, kind):
+    """Both stages on the paired-window format (lut_pw.cuh): one sort + one block per window serves two rotations."""
+    if kind == "shipped":
+        luts = orc.load_luts(util.lut_dir("lerf-g" if oC == 3 else "lerf-l"), linear=(oC == 1))
+    else:
+        luts = util.random_luts(41 + oC, oC2=oC)
+    rng = np.random.default_rng(15)
+    img = rng.integers(0, 256, size=(35, 41, 3)).astype(np.uint8)
+    img[:6, :6] = 255
+    img[6:10, :8] = (np.arange(8) * 16)[None, :, None]
+    img[10:14, :8] = 7
+    feat, codes, _ = orc.lut_stages(img, luts, oC=oC)
+    chw = np.ascontiguousarray(np.transpose(img, (2, 0, 1)))
+    t1 = [luts["s1_%sr0" % m] for m in "sct"]
+    t2 = []
+    for m in "sct":
+        t2 += [luts["s2_%sr0" % m], luts["s2_%sr1" % m]]
+
+    def run(stage, tables, oc, src):
+        tabs = [np.ascontiguousarray(t, dtype=np.int8) for t in tables]
+        arr = (ctypes.c_void_p * len(tabs))(*[t.ctypes.data for t in tabs])
+        out = np.empty((src.shape[0] * oc, src.shape[1], src.shape[2]), dtype=np.uint8)
+        s = np.ascontiguousarray(src)
+        assert emul.emul_stage_pw(stage, arr, oc, ctypes.c_void_p(s.ctypes.data), s.shape[0], s.shape[1], s.shape[2],
+                                  ctypes.c_void_p(out.ctypes.data)) == 0
+        return out
+
+    assert np.array_equal(run(1, t1, 1, chw), feat)
+    assert np.array_equal(run(2, t2, oC, feat), codes)
