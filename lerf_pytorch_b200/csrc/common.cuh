@@ -69,6 +69,10 @@ struct lerf_luts_impl {
   size_t pw_block_bytes;
   const uint8_t* pw1[6];
   const uint8_t* pw2[6];
+  // cell-pair copies (lut_pw.cu FmtCP, oC = 1): 6 families x 65536 blocks of 32 B; cp2 only for oC2 == 1
+  void* cp_block;
+  const uint8_t* cp1[6];
+  const uint8_t* cp2[6];
 };
 
 struct lerf_sr_plan_impl {

@@ -152,6 +152,7 @@ int lerf_luts_create(const int8_t* const host_tables[9], int oC2, int device, le
   int rc = build_cell_tables(L, host_tables);
   if (!rc) rc = build_pw_tables(L);
   if (rc) {
+    cudaFree(L->cp_block);
     cudaFree(L->pw_block);
     cudaFree(L->mt_block);
     cudaFree(L->cell_block);
@@ -175,6 +176,7 @@ void lerf_luts_destroy(lerf_luts_t* luts) {
   cudaFree(L->cell_block);
   cudaFree(L->mt_block);
   cudaFree(L->pw_block);
+  cudaFree(L->cp_block);
   delete L;
 }
 

@@ -35,13 +35,31 @@ struct Tables {
 __global__ void pw_repack_kernel(const int8_t* __restrict__ T, int oC, int entry_stride, int f, uint8_t* __restrict__ dst) {
   const uint32_t cellidx = blockIdx.x * blockDim.x + threadIdx.x;  // 65536 cells
   const uint32_t code = blockIdx.y;                                // 64 codes
-  uint8_t blk[32];
+  __align__(16) uint8_t blk[32];
   if (!pw::fill_block(T, oC, entry_stride, f, cellidx, code, blk)) return;
   const size_t B = pw::block_bytes(oC);
   uint4* o = reinterpret_cast<uint4*>(dst + (((size_t)code << 16) | cellidx) * B);
   const uint4* s = reinterpret_cast<const uint4*>(blk);
   o[0] = s[0];
   if (oC == 3) o[1] = s[1];
+}
+
+// cell-pair table of family f (oC = 1): block `cell` = [orientation 0: 16 corners][orientation 1: 16 corners], corner m of
+// the CANONICAL window at byte cell::corner_pos(m) of its half
+__global__ void cp_repack_kernel(const int8_t* __restrict__ T, int f, uint8_t* __restrict__ dst) {
+  const uint32_t cellidx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int msb[4] = {(int)((cellidx >> 12) & 15u), (int)((cellidx >> 8) & 15u), (int)((cellidx >> 4) & 15u), (int)(cellidx & 15u)};
+  __align__(16) uint8_t blk[32];
+  for (int o = 0; o < 2; ++o)
+    for (int m = 0; m < 16; ++m) {
+      const int bump[4] = {(m >> 3) & 1, (m >> 2) & 1, (m >> 1) & 1, m & 1};
+      int row = 0;
+      for (int k = 0; k < 4; ++k) row = row * 17 + msb[pw::pi_of(f, o, k)] + bump[pw::pi_of(f, o, k)];
+      blk[16 * o + cell::corner_pos(m)] = (uint8_t)T[row];
+    }
+  uint4* d = reinterpret_cast<uint4*>(dst + (size_t)cellidx * 32);
+  d[0] = reinterpret_cast<const uint4*>(blk)[0];
+  d[1] = reinterpret_cast<const uint4*>(blk)[1];
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -71,41 +89,73 @@ struct Pk<1> {
 };
 
 // LD: 0 = ld.global.nc (allocates in L1), 1 = nc + L1::no_allocate
-template <int OC, int LD>
-__device__ __forceinline__ void fetch(const uint8_t* __restrict__ tab, uint32_t block, uint32_t* q) {
-  if (OC == 3) {
-    const uint8_t* p = tab + (size_t)block * 32;
-    if (LD == 1)
-      asm("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-          : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])
-          : "l"(p));
-    else
-      asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-          : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])
-          : "l"(p));
-  } else {
-    const uint8_t* p = tab + (size_t)block * 16;
-    if (LD == 1)
-      asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]) : "l"(p));
-    else
-      asm("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]) : "l"(p));
-  }
+template <int LD>
+__device__ __forceinline__ void ld32(const uint8_t* p, uint32_t* q) {
+  if (LD == 1)
+    asm("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])
+        : "l"(p));
+  else
+    asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])
+        : "l"(p));
+}
+template <int LD>
+__device__ __forceinline__ void ld16(const uint8_t* p, uint32_t* q) {
+  if (LD == 1)
+    asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]) : "l"(p));
+  else
+    asm("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]) : "l"(p));
 }
 
+// Table formats of the window kernel.
+//   FmtPW<OC>: paired-window blocks keyed by (cell, LSB order) (lut_pw.cuh) -- no reuse between neighbours, fetched
+//              around L1.  Production for stage 2 of LeRF-G: the kernel is bound by sectors through the L2 -> L1 link.
+//   FmtCP:     "cell pair", oC = 1: the 16 corners of the cell for both orientations (2 x 16 bytes, lut_cell.cuh corner
+//              order) keyed by the cell alone -- 2 MiB per table, so neighbouring windows hit L1 like the per-pixel
+//              cell kernel does, but one sort and one 256-bit load serve two lookups.
 template <int OC>
-__device__ __forceinline__ void blend(const uint32_t* q, const pw::Lookup& L, Pk<OC>& o0, Pk<OC>& o1) {
-  if (OC == 3) {
-    int n[2][3] = {{0, 0, 0}, {0, 0, 0}};
-    pw::blend3(q, L, n);
-    o0.set(n[0]);
-    o1.set(n[1]);
-  } else {
-    int n[2] = {0, 0};
-    pw::blend1(q, L, n);
-    o0.set(&n[0]);
-    o1.set(&n[1]);
+struct FmtPW {
+  using Lookup = pw::Lookup;
+  static constexpr int nq = OC == 3 ? 8 : 4;
+  static constexpr int kDefaultLD = 1;
+  __device__ static __forceinline__ Lookup prepare(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return pw::prepare(a, b, c, d); }
+  template <int LD>
+  __device__ static __forceinline__ void fetch(const uint8_t* __restrict__ tab, const Lookup& L, uint32_t* q) {
+    if (OC == 3) ld32<LD>(tab + (size_t)L.block * 32, q);
+    else ld16<LD>(tab + (size_t)L.block * 16, q);
   }
-}
+  __device__ static __forceinline__ void blend(const uint32_t* q, const Lookup& L, Pk<OC>& o0, Pk<OC>& o1) {
+    if (OC == 3) {
+      int n[2][3] = {{0, 0, 0}, {0, 0, 0}};
+      pw::blend3(q, L, n);
+      o0.set(n[0]);
+      o1.set(n[1]);
+    } else {
+      int n[2] = {0, 0};
+      pw::blend1(q, L, n);
+      o0.set(&n[0]);
+      o1.set(&n[1]);
+    }
+  }
+};
+
+struct FmtCP {
+  using Lookup = cell::Simplex;
+  static constexpr int nq = 8;
+  static constexpr int kDefaultLD = 0;
+  __device__ static __forceinline__ Lookup prepare(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return cell::simplex_of(a, b, c, d, cell::Hash{0u, 0u, 0u});
+  }
+  template <int LD>
+  __device__ static __forceinline__ void fetch(const uint8_t* __restrict__ tab, const Lookup& L, uint32_t* q) {
+    ld32<LD>(tab + (size_t)L.cell * 32, q);
+  }
+  __device__ static __forceinline__ void blend(const uint32_t* q, const Lookup& L, Pk<1>& o0, Pk<1>& o1) {
+    o0.a = cell::blend(q[0], q[1], q[2], q[3], L);
+    o1.a = cell::blend(q[4], q[5], q[6], q[7], L);
+  }
+};
 
 __device__ __forceinline__ bool in_tile(int x, int y) { return (unsigned)x < (unsigned)kT && (unsigned)y < (unsigned)kT; }
 
@@ -139,13 +189,13 @@ struct Grp {
 // table loads are issued before the first one is consumed (the kernel lives on load latency: ncu r2a, long_scoreboard).
 // Exchange arrays (each written exactly once per tile pixel, so plain stores and a single barrier before the final
 // sum):  X[0] S0.o1 (+1,+1)   X[1] S1.o0 (+1,0)   X[2] S1.o1 (0,+1)   X[3] CH (+3,0)   X[4] CV (0,+3)   X[5] TD (+3,+3)   X[6] TA (-3,+3)
-template <int OC, int LD, int G>
+template <typename Fmt, int OC, int LD, int G>
 __device__ __forceinline__ void group_pass(const Tables& t, const uint32_t* __restrict__ tile, Pk<OC>* __restrict__ X, int tx,
                                            int tq, int tid, Pk<OC> own[4]) {
   using Gr = Grp<G>;
-  constexpr int nq = OC == 3 ? 8 : 4;
+  constexpr int nq = Fmt::nq;
   constexpr int kPx = kT * kT;
-  pw::Lookup L[5];
+  typename Fmt::Lookup L[5];
   uint32_t q[5][nq];
   int hx = 0, hy = 0;
   const bool h = tid < Gr::nhalo;
@@ -155,15 +205,15 @@ __device__ __forceinline__ void group_pass(const Tables& t, const uint32_t* __re
     if (j == 4 && !h) break;
     const int ax = j < 4 ? tx : hx, ay = j < 4 ? tq + 8 * j : hy;
     const uint32_t* c = tile + (ay + kHalo) * kPitch + ax + kHalo;
-    L[j] = pw::prepare(c[0], c[Gr::o1], c[Gr::o2], c[Gr::o3]);
-    fetch<OC, LD>(t.t[G == 0 ? 0 : G + 1], L[j].block, q[j]);
+    L[j] = Fmt::prepare(c[0], c[Gr::o1], c[Gr::o2], c[Gr::o3]);
+    Fmt::template fetch<LD>(t.t[G == 0 ? 0 : G + 1], L[j], q[j]);
   }
 #pragma unroll
   for (int j = 0; j < 5; ++j) {
     if (j == 4 && !h) break;
     const int ax = j < 4 ? tx : hx, ay = j < 4 ? tq + 8 * j : hy;
     Pk<OC> f, r;
-    blend<OC>(q[j], L[j], f, r);
+    Fmt::blend(q[j], L[j], f, r);
     if (j < 4) own[j].add(f);
     const int dx = ax + Gr::ddx, dy = ay + Gr::ddy;
     if (in_tile(dx, dy)) X[(G == 0 ? 0 : G + 2) * kPx + dy * kT + dx] = r;
@@ -172,21 +222,21 @@ __device__ __forceinline__ void group_pass(const Tables& t, const uint32_t* __re
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
       if (j == 4 && !h) break;
-      fetch<OC, LD>(t.t[1], L[j].block, q[j]);
+      Fmt::template fetch<LD>(t.t[1], L[j], q[j]);
     }
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
       if (j == 4 && !h) break;
       const int ax = j < 4 ? tx : hx, ay = j < 4 ? tq + 8 * j : hy;
       Pk<OC> b0, b1;
-      blend<OC>(q[j], L[j], b0, b1);
+      Fmt::blend(q[j], L[j], b0, b1);
       if (in_tile(ax + 1, ay)) X[1 * kPx + ay * kT + ax + 1] = b0;
       if (in_tile(ax, ay + 1)) X[2 * kPx + (ay + 1) * kT + ax] = b1;
     }
   }
 }
 
-template <int STAGE, int OC, int LD, int MINB>
+template <typename Fmt, int STAGE, int OC, int LD, int MINB>
 __global__ void __launch_bounds__(256, MINB)
     lut_stage_pw_kernel(Tables t, const uint8_t* __restrict__ in, InAddr ia, int H, int W, int y0, int y1,
                         uint8_t* __restrict__ out) {
@@ -206,11 +256,11 @@ __global__ void __launch_bounds__(256, MINB)
   Pk<OC> own[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) own[j].zero();
-  group_pass<OC, LD, 0>(t, tile, X, tx, tq, tid, own);
-  group_pass<OC, LD, 1>(t, tile, X, tx, tq, tid, own);
-  group_pass<OC, LD, 2>(t, tile, X, tx, tq, tid, own);
-  group_pass<OC, LD, 3>(t, tile, X, tx, tq, tid, own);
-  group_pass<OC, LD, 4>(t, tile, X, tx, tq, tid, own);
+  group_pass<Fmt, OC, LD, 0>(t, tile, X, tx, tq, tid, own);
+  group_pass<Fmt, OC, LD, 1>(t, tile, X, tx, tq, tid, own);
+  group_pass<Fmt, OC, LD, 2>(t, tile, X, tx, tq, tid, own);
+  group_pass<Fmt, OC, LD, 3>(t, tile, X, tx, tq, tid, own);
+  group_pass<Fmt, OC, LD, 4>(t, tile, X, tx, tq, tid, own);
   __syncthreads();
 
   const int x = bx + tx;
@@ -261,6 +311,20 @@ int build_pw_tables(lerf_luts_impl* L) {
     L->pw1[f] = d1;
     L->pw2[f] = d2;
   }
+  // cell-pair tables (oC = 1 only): stage 1 always, stage 2 for LeRF-L
+  const size_t cpb = (size_t)65536 * 32;
+  e = cudaMalloc(&L->cp_block, (oC == 1 ? 12 : 6) * cpb);
+  if (e != cudaSuccess) return fail(LERF_ENOMEM, "cudaMalloc for the cell-pair LUT block failed: %s", cudaGetErrorString(e));
+  for (int f = 0; f < 6; ++f) {
+    uint8_t* d1 = (uint8_t*)L->cp_block + f * cpb;
+    pwk::cp_repack_kernel<<<65536 / 256, 256>>>(L->s1[f >> 1], f, d1);
+    L->cp1[f] = d1;
+    if (oC == 1) {
+      uint8_t* d2 = (uint8_t*)L->cp_block + (6 + f) * cpb;
+      pwk::cp_repack_kernel<<<65536 / 256, 256>>>((const int8_t*)L->s2[f], f, d2);
+      L->cp2[f] = d2;
+    }
+  }
   e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return fail(LERF_ECUDA, "paired-window LUT repack failed: %s", cudaGetErrorString(e));
   return LERF_OK;
@@ -269,36 +333,54 @@ int build_pw_tables(lerf_luts_impl* L) {
 int launch_stage_pw(const lerf_luts_impl* L, int stage, const uint8_t* in, const InAddr& ia, int planes, int H, int W,
                     int y0, int y1, uint8_t* out, int variant, cudaStream_t st) {
   if (!L->pw_block) return fail(LERF_EUNSUPPORTED, "paired-window tables were not built for this LUT set");
+  const bool cp = variant >= 10;  // variants 10+: cell-pair format (oC = 1)
+  if (cp && stage == 2 && L->oC2 != 1) return fail(LERF_EUNSUPPORTED, "cell-pair tables exist for oC = 1 only");
   pwk::Tables t;
-  for (int i = 0; i < 6; ++i) t.t[i] = stage == 1 ? L->pw1[i] : L->pw2[i];
+  for (int i = 0; i < 6; ++i) t.t[i] = cp ? (stage == 1 ? L->cp1[i] : L->cp2[i]) : (stage == 1 ? L->pw1[i] : L->pw2[i]);
   dim3 grid((W + pwk::kT - 1) / pwk::kT, (y1 - y0 + pwk::kT - 1) / pwk::kT, planes);
-#define LERF_GO(S, O, LD, B)                                                                                      \
+#define LERF_GO(F, S, O, LD, B)                                                                                   \
   {                                                                                                               \
     static bool attr_set = false; /* per instantiation: > 48 KB of dynamic shared memory needs the opt-in */       \
     if (!attr_set) {                                                                                              \
-      LERF_CUDA(cudaFuncSetAttribute(pwk::lut_stage_pw_kernel<S, O, LD, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      LERF_CUDA(cudaFuncSetAttribute(pwk::lut_stage_pw_kernel<F, S, O, LD, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)pwk::smem_bytes<O>()));                                                 \
       attr_set = true;                                                                                            \
     }                                                                                                             \
-    pwk::lut_stage_pw_kernel<S, O, LD, B><<<grid, 256, pwk::smem_bytes<O>(), st>>>(t, in, ia, H, W, y0, y1, out);  \
+    pwk::lut_stage_pw_kernel<F, S, O, LD, B><<<grid, 256, pwk::smem_bytes<O>(), st>>>(t, in, ia, H, W, y0, y1, out); \
   }
-  if (stage == 1) {
+  using pwk::FmtCP;
+  using pwk::FmtPW;
+  if (cp) {
+    if (stage == 1) {
+      switch (variant) {
+        case 11: LERF_GO(FmtCP, 1, 1, 0, 3) break;
+        case 12: LERF_GO(FmtCP, 1, 1, 0, 5) break;
+        case 13: LERF_GO(FmtCP, 1, 1, 1, 4) break;
+        default: LERF_GO(FmtCP, 1, 1, 0, 4)
+      }
+    } else {
+      switch (variant) {
+        case 11: LERF_GO(FmtCP, 2, 1, 0, 3) break;
+        default: LERF_GO(FmtCP, 2, 1, 0, 4)
+      }
+    }
+  } else if (stage == 1) {
     switch (variant) {
-      case 1: LERF_GO(1, 1, 0, 3) break;
-      case 2: LERF_GO(1, 1, 1, 4) break;
-      case 3: LERF_GO(1, 1, 0, 4) break;
-      default: LERF_GO(1, 1, 1, 3)
+      case 1: LERF_GO(FmtPW<1>, 1, 1, 0, 3) break;
+      case 2: LERF_GO(FmtPW<1>, 1, 1, 1, 4) break;
+      case 3: LERF_GO(FmtPW<1>, 1, 1, 0, 4) break;
+      default: LERF_GO(FmtPW<1>, 1, 1, 1, 3)
     }
   } else if (L->oC2 == 3) {
     switch (variant) {
-      case 1: LERF_GO(2, 3, 0, 3) break;
-      case 2: LERF_GO(2, 3, 1, 2) break;
-      default: LERF_GO(2, 3, 1, 3)
+      case 1: LERF_GO(FmtPW<3>, 2, 3, 0, 3) break;
+      case 2: LERF_GO(FmtPW<3>, 2, 3, 1, 2) break;
+      default: LERF_GO(FmtPW<3>, 2, 3, 1, 3)
     }
   } else {
     switch (variant) {
-      case 1: LERF_GO(2, 1, 0, 3) break;
-      default: LERF_GO(2, 1, 1, 3)
+      case 1: LERF_GO(FmtPW<1>, 2, 1, 0, 3) break;
+      default: LERF_GO(FmtPW<1>, 2, 1, 1, 3)
     }
   }
 #undef LERF_GO

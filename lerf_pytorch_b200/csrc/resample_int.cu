@@ -39,15 +39,66 @@ __global__ void __launch_bounds__(kCX* kCY, MINB)
                                  blockIdx.z, sm);
 }
 
+// uint8 outputs through a staged tile (resample_int.cuh): CH = 1 planar, CH = 3 interleaved
+template <int S, int CH, bool CG>
+__global__ void __launch_bounds__(kCX* kCY, 4)
+    resize_sr_int_gauss_u8_kernel(const uint8_t* __restrict__ feat, const uint8_t* __restrict__ codes, int H, int W, int oH,
+                                  int oW, const __grid_constant__ IntGeom<S> g, const CoefTabs* __restrict__ ct, int ly0,
+                                  int oy0, int oy1, unsigned char* __restrict__ out) {
+  __shared__ Smem sm;
+  __shared__ OutTile<S, CH> ot;
+  resize_int_u8_body<S, CH, CG>(feat, codes, H, W, oH, oW, g, ct, ly0, oy0, oy1, out, blockIdx.x, blockIdx.y, blockIdx.z, sm, ot);
+}
+
+template <int S, bool CG>
+__global__ void __launch_bounds__(kCX* kCY, 4)
+    resize_sr_int_gauss_u8p_kernel(const uint8_t* __restrict__ feat, const uint8_t* __restrict__ codes, int H, int W, int oH,
+                                   int oW, const __grid_constant__ IntGeom<S> g, const CoefTabs* __restrict__ ct, int ly0,
+                                   int oy0, int oy1, unsigned char* __restrict__ out) {
+  __shared__ Smem sm;
+  resize_int_u8_planar_body<S, CG>(feat, codes, H, W, oH, oW, g, ct, ly0, oy0, oy1, out, blockIdx.x, blockIdx.y, blockIdx.z, sm);
+}
+
+int g_u8_staged = 1;  // testing hook: 0 = the byte-store epilogue of r1
+
 template <int S>
 static int launch_int(const lerf_sr_plan_impl* P, const uint8_t* feat, const uint8_t* codes, int planes, int channels,
                       float max_sigma, int oy0, int oy1, void* out, int fmt, cudaStream_t st) {
-  const IntGeom<S> g = make_geom<S>(P, max_sigma, /*unsigned_form=*/g_variant == 0 || g_variant == 4);
+  const IntGeom<S> g = make_geom<S>(P, max_sigma, /*unsigned_form=*/g_variant == 0 || g_variant == 4 || g_variant == 11);
   const CoefTabs* ct = plan_coef_tabs(P, max_sigma, st);
   if (!ct) return fail(LERF_ECUDA, "uploading the hyper decode tables failed");
   // cell rows touched by the output band
   const int ly0 = P->h_left_y[oy0], ly1 = P->h_left_y[oy1 - 1];
   dim3 block(kCX * kCY), grid((P->W + 1 + kCX - 1) / kCX, (ly1 - ly0 + 1 + kCY - 1) / kCY, planes);
+  const bool cg = g_variant == 0 && geom_is_constexpr<S>(P);  // geometry factors as immediates (resample_int.cuh CGeom)
+  // staged uint8 epilogue: the tile must fit the 48 KiB of static shared memory next to the coefficient tiles
+  if (g_u8_staged && (g_variant == 0 || g_variant == 11)) {
+    if constexpr (S == 4 || S == 8) {  // planar: aligned words through a lane shuffle (x4) or as they are (x8)
+      if (fmt == LERF_OUT_U8 && g.ph_x == S / 2 && P->oW % 4 == 0 && ((uintptr_t)out & 3) == 0) {
+        if (cg) resize_sr_int_gauss_u8p_kernel<S, true><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, ly0, oy0, oy1, (unsigned char*)out);
+        else resize_sr_int_gauss_u8p_kernel<S, false><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, ly0, oy0, oy1, (unsigned char*)out);
+        LERF_LAUNCHED();
+        return LERF_OK;
+      }
+    }
+    if constexpr (S != 4 && S != 8) {  // planar at x2 / x3: the staged tile
+      if (fmt == LERF_OUT_U8) {
+        if (cg) resize_sr_int_gauss_u8_kernel<S, 1, true><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, ly0, oy0, oy1, (unsigned char*)out);
+        else resize_sr_int_gauss_u8_kernel<S, 1, false><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, ly0, oy0, oy1, (unsigned char*)out);
+        LERF_LAUNCHED();
+        return LERF_OK;
+      }
+    }
+    if constexpr (sizeof(OutTile<S, 3>) + sizeof(Smem) <= 48 * 1024) {
+      if (fmt == LERF_OUT_U8_HWC && channels == 3 && planes % 3 == 0) {
+        grid.z = planes / 3;
+        if (cg) resize_sr_int_gauss_u8_kernel<S, 3, true><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, ly0, oy0, oy1, (unsigned char*)out);
+        else resize_sr_int_gauss_u8_kernel<S, 3, false><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, ly0, oy0, oy1, (unsigned char*)out);
+        LERF_LAUNCHED();
+        return LERF_OK;
+      }
+    }
+  }
 #define LERF_GK(F, HO, B)                                                                                              \
   resize_sr_int_gauss_kernel<S, F, HO, B><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, \
                                                                   channels, ly0, oy0, oy1, out)
@@ -56,6 +107,7 @@ static int launch_int(const lerf_sr_plan_impl* P, const uint8_t* feat, const uin
   else if (g_variant == 2) LERF_GK(F, 0, 4);         \
   else if (g_variant == 5) LERF_GK(F, 0, 5);         \
   else if (g_variant == 4) LERF_GK(F, 2, 5);         \
+  else if (cg) LERF_GK(F, 3, 4);                     \
   else LERF_GK(F, 2, 4)
   switch (fmt) {
     case LERF_OUT_F32: LERF_GO(LERF_OUT_F32); break;
@@ -83,7 +135,10 @@ int resize_sr_int_gauss(const lerf_sr_plan_impl* P, const uint8_t* feat, const u
   }
 }
 
-void resize_int_config(int variant) { g_variant = variant; }
+void resize_int_config(int variant) {  // 10: production arithmetic with the byte-store uint8 epilogue of r1; 11: geometry from kernel parameters (r1)
+  g_u8_staged = variant != 10;
+  g_variant = variant == 10 ? 0 : variant;
+}
 
 }  // namespace lerf
 

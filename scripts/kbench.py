@@ -38,7 +38,7 @@ def timeit(fn):
 for kind in os.environ.get("KB_KINDS", "natural,uniform").split(","):
     frames = (bench.natural_frames_gpu if kind == "natural" else bench.uniform_frames_gpu)(B, 3000, dev)
     ref_feat = None
-    s1_variants = ((0, "cell (production)"), (1, "row-major minb3"), (25, "cell minb5"), (26, "cell minb6"), (80, "pw minb3"), (81, "pw L1 minb3"), (82, "pw minb4"), (83, "pw L1 minb4"))
+    s1_variants = ((0, "cell (production)"), (1, "row-major minb3"), (25, "cell minb5"), (26, "cell minb6"), (80, "pw minb3"), (81, "pw L1 minb3"), (82, "pw minb4"), (83, "pw L1 minb4"), (90, "cell-pair minb4"), (91, "cell-pair minb3"), (92, "cell-pair minb5"), (93, "cell-pair noalloc"))
     if ONLY == "pw":
         s1_variants = tuple(x for x in s1_variants if x[0] == 0 or x[0] >= 80)
     for v, name in (s1_variants[:1] if ONLY == "prod" else s1_variants):
@@ -82,6 +82,19 @@ for kind in os.environ.get("KB_KINDS", "natural,uniform").split(","):
     for fmt in ("f32", "u8", "u8_hwc"):
         out = rs.resize_codes(ref_feat, codes, out_format=fmt)
         print("%-8s resize %-20s %8.1f us/frame" % (kind, "int-scale " + fmt, timeit(lambda: rs.resize_codes(ref_feat, codes, out_format=fmt, out=out))), flush=True)
+        if fmt == "f32":  # geometry factors from kernel parameters (r1) against immediates (r2)
+            L.lerf_debug_resize_variant(11)
+            o2 = rs.resize_codes(ref_feat, codes, out_format=fmt)
+            assert torch.equal(o2, out), "compile-time geometry changes the result"
+            print("%-8s resize %-20s %8.1f us/frame" % (kind, "int-scale f32 r1 geom", timeit(lambda: rs.resize_codes(ref_feat, codes, out_format=fmt, out=o2))), flush=True)
+            L.lerf_debug_resize_variant(0)
+        if fmt != "f32":  # the byte-store epilogue of r1 against the staged tile
+            L.lerf_debug_resize_variant(10)
+            o2 = rs.resize_codes(ref_feat, codes, out_format=fmt)
+            d = (o2.int() - out.int()).abs()  # single rounding (r2) against float32-then-integer (r1): rare .5 ties
+            assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 1e-4, "uint8 epilogues disagree"
+            print("%-8s resize %-20s %8.1f us/frame" % (kind, "int-scale " + fmt + " r1 bytes", timeit(lambda: rs.resize_codes(ref_feat, codes, out_format=fmt, out=o2))), flush=True)
+            L.lerf_debug_resize_variant(0)
     if ONLY not in ("prod", "pw"):
         out = rs.resize_codes(ref_feat, codes, out_format="f32")
         for v in (0, 1, 2, 4, 5):

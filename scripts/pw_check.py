@@ -33,8 +33,8 @@ for model, linear in (("lerf-g", False), ("lerf-l", True)):
                 L.lerf_debug_lut_variant(1, 0); L.lerf_debug_lut_variant(2, 70 if not linear else 0)
                 feat = lp.lut_stage1(luts, d)
                 codes = lp.lut_stage2(luts, feat)
-                for v in (80, 81):
-                    L.lerf_debug_lut_variant(1, v); L.lerf_debug_lut_variant(2, v)
+                for v in (80, 81, 90, 91, 92):
+                    L.lerf_debug_lut_variant(1, v); L.lerf_debug_lut_variant(2, v if (v < 90 or (linear and v < 92)) else 80)
                     f2 = lp.lut_stage1(luts, d)
                     c2 = lp.lut_stage2(luts, feat)
                     ok = torch.equal(f2, feat) and torch.equal(c2, codes)
