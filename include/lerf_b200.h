@@ -12,6 +12,7 @@
  * this path is three Python call signatures.  Each function below names the reference
  * interface it replaces (file:line in the reference tree); INTEGRATION.md shows the
  * ctypes binding a maintainer adds behind those Python signatures.
+ * Test and tuning switches are NOT part of this interface: they live in lerf_b200_testing.h.
  *
  * Layouts
  *   image planes : uint8 or float32, planar [P][H][W]; P = batch * channels, every plane is
@@ -104,13 +105,6 @@ int lerf_lut_stage1(const lerf_luts_t* luts, const uint8_t* in, int planes, int 
 int lerf_lut_stage2(const lerf_luts_t* luts, const uint8_t* feat, int planes, int H, int W, int y0,
                     int y1, uint8_t* codes, lerf_stream_t stream);
 
-/* Testing / tuning hook: selects the kernel behind lerf_lut_stage1 (stage = 1) / lerf_lut_stage2 (stage = 2).
- * 0 = production choice; 1..19 = the row-major-table kernel (first implementation, kept for A/B); 20+ = tuning
- * variants of the cell-packed-table kernel.  All non-experimental variants produce identical bytes. */
-void lerf_debug_lut_variant(int stage, int variant);
-/* Testing / tuning hook: weights of the cell-block swizzle baked into the tables by the NEXT lerf_luts_create
- * (0,0,0 = plain layout; default 9,5,3).  Results never depend on it. */
-void lerf_debug_cell_hash(int ha, int hb, int hc);
 
 /* ---- SR geometry plan --------------------------------------------------------------------------
  * Replaces Resize2dNumpy.set_shape / get_distance (resize_right2d_numpy.py:18-140) for support 2.
@@ -136,19 +130,6 @@ int lerf_resize_sr(int kind, const lerf_sr_plan_t* plan, const uint8_t* feat, co
                    int planes, int channels, float max_sigma, int oy0, int oy1, void* out,
                    int out_format, lerf_stream_t stream);
 
-/* Testing hook.  0 = production dispatch (cell-owner kernel for integer scales, tile kernel for other scales >= 1,
- * fast warp kernel); 1 = only the float64 operation-order kernels (the parity path); 2 = like 0 without the cell-owner
- * kernel, so integer scales take the tile kernel too.  All must agree within the fp32 tolerance. */
-void lerf_debug_force_generic(int on);
-
-/* Testing hook for lerf_warp's fast Gaussian kernel: 1 (default) = every input sample is first decoded into a 32-byte
- * record (stream-ordered scratch from cudaMallocAsync) and a tap is one 256-bit gather; 0 = taps are gathered from
- * feat/codes and decoded through tables.  Same arithmetic, identical results. */
-void lerf_debug_warp_records(int on);
-
-/* Testing / tuning hook for the integer-scale kernel: 0 = production form; 1 = hoisted-FP64 form (80 registers);
- * 2 = production form at a 64-register budget.  All forms stay within the 1e-4 bar. */
-void lerf_debug_resize_variant(int variant);
 
 /* Same operator on float32 image / float32 hyper planes in [0,1], for callers that bring their own
  * (non-LUT) hyper-parameters exactly like the reference's resize(input, rho, sigma_x, sigma_y).
@@ -196,9 +177,6 @@ int lerf_sr_fused(const lerf_luts_t* luts, int kind, const lerf_sr_plan_t* plan,
                   long long in_row_stride, long long in_pix_stride, float max_sigma, int oy0, int oy1,
                   void* scratch, void* out, int out_format, lerf_stream_t stream);
 
-/* Testing / tuning hook for lerf_sr_fused: enabled = 0 forces the three plain launches; min_blocks (2..4) and
- * group_planes (0 = auto) tune the role-interleaved pipeline kernel.  Results never depend on it. */
-void lerf_debug_pipeline(int enabled, int min_blocks, int group_planes);
 
 /* Number of kernel launches issued by this library on the calling thread since the last reset
  * (bench.py reports it as gpu_launches). */

@@ -7,7 +7,10 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblerf_b200.so")
+# LERF_B200_EXPERIMENTS=1 (scripts/kbench.py, A/B runs) loads the build with every tuning variant compiled in
+# (`python -m lerf_pytorch_b200.build --experiments`); everything else uses the product library.
+EXPERIMENTS = os.environ.get("LERF_B200_EXPERIMENTS", "") not in ("", "0")
+LIB_PATH = os.path.join(HERE, "liblerf_b200_exp.so" if EXPERIMENTS else "liblerf_b200.so")
 
 LERF_KIND_GAUSS, LERF_KIND_LINEAR = 0, 1
 LERF_OUT_F32, LERF_OUT_U8, LERF_OUT_U8_HWC = 0, 1, 2
@@ -29,11 +32,6 @@ PROTOTYPES = {
     "lerf_sr_plan_create": (_c_i, [_c_i, _c_i, _c_i, _c_i, _c_p, _c_p, _c_p, _c_p, _c_i, _c_p]),
     "lerf_sr_plan_destroy": (None, [_c_p]),
     "lerf_resize_sr": (_c_i, [_c_i, _c_p, _c_p, _c_p, _c_i, _c_i, _c_f, _c_i, _c_i, _c_p, _c_i, _c_p]),
-    "lerf_debug_force_generic": (None, [_c_i]),
-    "lerf_debug_warp_records": (None, [_c_i]),
-    "lerf_debug_resize_variant": (None, [_c_i]),
-    "lerf_debug_lut_variant": (None, [_c_i, _c_i]),
-    "lerf_debug_cell_hash": (None, [_c_i, _c_i, _c_i]),
     "lerf_resize_sr_f32": (_c_i, [_c_i, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_f, _c_p, _c_p]),
     "lerf_warp": (_c_i, [_c_i, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p, _c_i, _c_i, _c_f, _c_p, _c_i,
                          _c_p, _c_i, _c_i, _c_i, _c_p]),
@@ -44,9 +42,21 @@ PROTOTYPES = {
     "lerf_sr_scratch_bytes": (_c_sz, [_c_i, _c_i, _c_i, _c_i]),
     "lerf_sr_fused": (_c_i, [_c_p, _c_i, _c_p, _c_p, _c_i, _c_i, _c_ll, _c_ll, _c_ll, _c_ll, _c_f, _c_i, _c_i, _c_p,
                              _c_p, _c_i, _c_p]),
-    "lerf_debug_pipeline": (None, [_c_i, _c_i, _c_i]),
     "lerf_launch_count": (_c_ll, []),
     "lerf_launch_count_reset": (None, []),
+}
+
+# include/lerf_b200_testing.h: test / tuning switches, not part of the drop-in interface
+TESTING_PROTOTYPES = {
+    "lerf_build_has_experiments": (_c_i, []),
+    "lerf_debug_lut_variant": (None, [_c_i, _c_i]),
+    "lerf_debug_cell_hash": (None, [_c_i, _c_i, _c_i]),
+    "lerf_debug_force_generic": (None, [_c_i]),
+    "lerf_debug_warp_records": (None, [_c_i]),
+    "lerf_debug_resize_variant": (None, [_c_i]),
+    "lerf_debug_pipeline": (None, [_c_i, _c_i, _c_i]),
+    "lerf_debug_l2_window": (None, [_c_i]),
+    "lerf_debug_carveout": (None, [_c_i]),
 }
 
 _lib = None
@@ -65,7 +75,7 @@ def lib():
                 "lerf_pytorch_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
         L = ctypes.CDLL(LIB_PATH)
-        for name, (res, args) in PROTOTYPES.items():
+        for name, (res, args) in list(PROTOTYPES.items()) + list(TESTING_PROTOTYPES.items()):
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args

@@ -7,6 +7,7 @@
 #include <string>
 
 #include "lerf_b200.h"
+#include "lerf_b200_testing.h"
 
 namespace lerf {
 
@@ -14,6 +15,22 @@ extern thread_local std::string g_last_error;
 extern thread_local long long g_launches;
 
 int fail(int code, const char* fmt, ...);
+
+// Test / tuning switches behind include/lerf_b200_testing.h.  They live in ONE thread-local struct: a hook only changes
+// the kernels that the calling thread launches afterwards, never another thread's.  Variants marked (x) exist only in a
+// library built with -DLERF_EXPERIMENTS (build.py: liblerf_b200_exp.so); the product library ignores them.
+struct DebugState {
+  int lut_variant[2] = {0, 0};    // per stage, see lerf_debug_lut_variant
+  int cell_hash[3] = {9, 5, 3};   // swizzle baked into the NEXT LutSet's cell tables
+  int resize_variant = 0;         // integer-scale resampler flavour
+  int u8_staged = 1;              // 0 = byte-store uint8 epilogue of r1
+  int force_generic = 0;          // 1 = float64 parity kernels only; 2 = no cell-owner kernel
+  int warp_records = 1;           // 0 = table form of the fast warp kernel
+  int pipe_enabled = 0, pipe_minb = 3, pipe_group = 0;  // (x) role-interleaved pipeline kernel
+  int l2_window = 0;              // lerf_luts_pin_l2: 0 = cell-packed block, 1 = paired-window block
+  int carveout = -1;              // shared-memory carve-out (percent) of the stage kernels, -1 = production
+};
+extern thread_local DebugState g_dbg;
 
 #define LERF_CUDA(expr)                                                                      \
   do {                                                                                       \
@@ -88,9 +105,10 @@ struct lerf_sr_plan_impl {
   double ph_dist_y[8][2], ph_dist_x[8][2];  // their distances to tap 0 / tap 1
   int tile_ok;     // every 32 x 32 output group has its taps in a 33 x 33 input window (any scale >= 1), |dist| <= 1: resample_tile.cu
   int tile_rows;   // output rows per block of the tile kernel: the largest of 128, 96, 64, 32 whose taps fit 33 input rows
-  void* coef_dev;    // rsi::CoefTabs for coef_sigma (resample_int.cu), allocated on first use
-  void* coef_host;
-  float coef_sigma;
+  static constexpr int kCoefSlots = 8;
+  void* coef_dev[kCoefSlots];    // rsi::CoefTabs per max_sigma (resample_int.cu plan_coef_tabs), immutable once uploaded
+  float coef_sigma[kCoefSlots];
+  int coef_n;
 };
 
 // lut_cell.cu
@@ -112,7 +130,6 @@ int launch_stage2_mt(const lerf_luts_impl* L, const uint8_t* feat, int planes, i
 // pipeline.cu
 int sr_pipeline(const lerf_luts_impl* L, int kind, const lerf_sr_plan_impl* P, const uint8_t* in, int planes, const InAddr& ia,
                 float max_sigma, int oy0, int oy1, uint8_t* feat, uint8_t* codes, void* out, int fmt, cudaStream_t st);
-void sr_pipeline_config(int enabled, int minb, int group_planes);
 
 // resample_int.cu
 int resize_sr_int_gauss(const lerf_sr_plan_impl* P, const uint8_t* feat, const uint8_t* codes, int planes, int channels,
@@ -121,7 +138,6 @@ int resize_sr_int_gauss(const lerf_sr_plan_impl* P, const uint8_t* feat, const u
 int resize_sr_int_linear(const lerf_sr_plan_impl* P, const uint8_t* feat, const uint8_t* codes, int planes, int channels,
                          float max_sigma, int oy0, int oy1, void* out, int fmt, cudaStream_t st);
 
-void resize_int_config(int variant);
 
 // resample_tile.cu: fast paths for uint8 code inputs; return -1 when they do not apply
 int resize_sr_tile(int kind, const lerf_sr_plan_impl* P, const uint8_t* feat, const uint8_t* codes, int planes, int channels,
@@ -129,6 +145,5 @@ int resize_sr_tile(int kind, const lerf_sr_plan_impl* P, const uint8_t* feat, co
 int warp_fast(int kind, const uint8_t* feat, const uint8_t* codes, int planes, int channels, int H, int W, int oH, int oW,
               const double minv[9], int pad0_y, int pad0_x, int mpad0_y, int mpad0_x, int border, float max_sigma, void* out,
               int fmt, uint8_t* mask, cudaStream_t st);
-void warp_fast_config(int use_records);
 
 }  // namespace lerf

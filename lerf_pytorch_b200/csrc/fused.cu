@@ -47,6 +47,10 @@ int lerf_sr_fused(const lerf_luts_t* luts, int kind, const lerf_sr_plan_t* plan,
 }
 
 /* Testing / tuning hook (see lerf_b200.h). */
-void lerf_debug_pipeline(int enabled, int min_blocks, int group_planes) { sr_pipeline_config(enabled, min_blocks, group_planes); }
+void lerf_debug_pipeline(int enabled, int min_blocks, int group_planes) {
+  g_dbg.pipe_enabled = enabled != 0;
+  g_dbg.pipe_minb = min_blocks;
+  g_dbg.pipe_group = group_planes;
+}
 
 }  // extern "C"

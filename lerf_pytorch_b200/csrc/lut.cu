@@ -23,6 +23,7 @@ namespace lerf {
 
 thread_local std::string g_last_error;
 thread_local long long g_launches = 0;
+thread_local DebugState g_dbg;
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -34,6 +35,7 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+#ifdef LERF_EXPERIMENTS  // first implementation of the stages on the shipped row-major tables, kept for A/B runs
 template <int STAGE, int OC, int MINB>
 __global__ void __launch_bounds__(rm::kTX* rm::kTY, (MINB >= 11 ? 3 : MINB))
     lut_stage_kernel(rm::StageTables tabs, const uint8_t* __restrict__ in, InAddr ia, int H, int W, int y0, int y1,
@@ -42,6 +44,7 @@ __global__ void __launch_bounds__(rm::kTX* rm::kTY, (MINB >= 11 ? 3 : MINB))
   rm::lut_stage_body<STAGE, OC, (MINB >= 11 ? MINB - 10 : 0)>(tabs, in, ia, H, W, y0, y1, out, blockIdx.x, blockIdx.y,
                                                              blockIdx.z, tile);
 }
+#endif
 
 // Generic single pass (any of the five modes, any oC): the drop-in for one call of
 // FourSimplexInterpFaster.  Slow path by design -- the product path uses the stage kernels.
@@ -92,8 +95,6 @@ static bool mode_taps(char mode, PassTaps& t, int& pad) {
 
 using namespace lerf;
 
-static int g_cell_hash[3] = {9, 5, 3};
-static int g_lut_variant[2] = {0, 0};  // per stage: 0 = production, 1..19 legacy row-major kernel, 20+ cell kernel
 
 extern "C" {
 
@@ -148,7 +149,7 @@ int lerf_luts_create(const int8_t* const host_tables[9], int oC2, int device, le
   }
   for (int i = 0; i < 3; ++i) L->s1[i] = (const int8_t*)((uint8_t*)L->block + i * s1_bytes);
   for (int i = 0; i < 6; ++i) L->s2[i] = (uint8_t*)L->block + 3 * s1_bytes + i * s2_bytes;
-  for (int i = 0; i < 3; ++i) L->cell_hash[i] = g_cell_hash[i];
+  for (int i = 0; i < 3; ++i) L->cell_hash[i] = g_dbg.cell_hash[i];
   int rc = build_cell_tables(L, host_tables);
   if (!rc) rc = build_pw_tables(L);
   if (rc) {
@@ -161,8 +162,9 @@ int lerf_luts_create(const int8_t* const host_tables[9], int oC2, int device, le
     return rc;
   }
   // Reserve persisting L2 for the tables (best effort; the window itself is per stream).
-  size_t want = L->cell_block_bytes;
-  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+  size_t want = L->cell_block_bytes, have = 0;
+  if (cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize) != cudaSuccess) have = 0;
+  if (want > have) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);  // only ever raise the device-wide limit
   cudaGetLastError();
   *out = reinterpret_cast<lerf_luts_t*>(L);
   return LERF_OK;
@@ -172,6 +174,8 @@ void lerf_luts_destroy(lerf_luts_t* luts) {
   if (!luts) return;
   lerf_luts_impl* L = reinterpret_cast<lerf_luts_impl*>(luts);
   cudaSetDevice(L->device);
+  cudaCtxResetPersistingL2Cache();  // lines this set's window marked persisting go back to normal
+  cudaGetLastError();
   cudaFree(L->block);
   cudaFree(L->cell_block);
   cudaFree(L->mt_block);
@@ -184,19 +188,35 @@ int lerf_luts_oc(const lerf_luts_t* luts) {
   return luts ? reinterpret_cast<const lerf_luts_impl*>(luts)->oC2 : 0;
 }
 
+// Best effort by contract: a device that offers no access-policy window (MIG slices, vGPU) or a smaller one is not an
+// error, the kernels do not need it.  What it buys on B200 is little in any case: the production tables are far smaller
+// than the 126 MB L2 and stay resident without help (ncu r2: L2 sector hit rate 96.9 % in stage 1, 93.9 % in a cold
+// single-frame stage-2 launch).
 int lerf_luts_pin_l2(const lerf_luts_t* luts, lerf_stream_t stream) {
   if (!luts) return fail(LERF_EINVAL, "lerf_luts_pin_l2: null handle");
   const lerf_luts_impl* L = reinterpret_cast<const lerf_luts_impl*>(luts);
+  int max_window = 0;
+  if (cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, L->device) != cudaSuccess || max_window <= 0) {
+    cudaGetLastError();
+    return LERF_OK;
+  }
+  const bool pw = g_dbg.l2_window == 1 && L->pw_block;
+  void* base = pw ? L->pw_block : L->cell_block;
+  size_t bytes = pw ? L->pw_block_bytes : L->cell_block_bytes;
+  if (bytes > (size_t)max_window) bytes = (size_t)max_window;
   cudaStreamAttrValue attr;
   memset(&attr, 0, sizeof(attr));
-  attr.accessPolicyWindow.base_ptr = L->cell_block;  // the tables the production kernels read
-  attr.accessPolicyWindow.num_bytes = L->cell_block_bytes;
-  attr.accessPolicyWindow.hitRatio = 1.0f;
+  attr.accessPolicyWindow.base_ptr = base;
+  attr.accessPolicyWindow.num_bytes = bytes;
+  attr.accessPolicyWindow.hitRatio = pw ? 0.25f : 1.0f;  // a quarter of the order planes of a table are ever touched
   attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
   attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  LERF_CUDA(cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+  if (cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
   return LERF_OK;
 }
+
+void lerf_debug_l2_window(int which) { g_dbg.l2_window = which; }
+void lerf_debug_carveout(int percent) { g_dbg.carveout = percent; }
 
 int lerf_lut_pass(const int8_t* table, const uint8_t* img, int C, int h, int w, char mode, int oC,
                   int32_t* out, lerf_stream_t stream) {
@@ -230,34 +250,38 @@ int lerf_lut_stage1(const lerf_luts_t* luts, const uint8_t* in, int planes, int 
   if (in_channels < 1) return fail(LERF_EINVAL, "lerf_lut_stage1: in_channels must be >= 1");
   if (planes == 0 || y0 == y1) return LERF_OK;
   const lerf_luts_impl* L = reinterpret_cast<const lerf_luts_impl*>(luts);
-  rm::StageTables t;
-  for (int i = 0; i < 3; ++i) t.t[i] = L->s1[i];
-  for (int i = 3; i < 6; ++i) t.t[i] = nullptr;
   InAddr ia{in_channels, in_batch_stride, in_chan_stride, in_row_stride, in_pix_stride};
-  if (g_lut_variant[0] >= 80)  // paired-window tables (lut_pw.cu)
-    return launch_stage_pw(L, 1, in, ia, planes, H, W, y0, y1, feat, g_lut_variant[0] - 80, (cudaStream_t)stream);
-  if (g_lut_variant[0] == 0 || g_lut_variant[0] >= 20)  // production: cell-packed tables (lut_cell.cu)
-    return launch_stage_cell(L, 1, in, ia, planes, H, W, y0, y1, feat, g_lut_variant[0] >= 20 ? g_lut_variant[0] - 20 : 0,
-                             (cudaStream_t)stream);
-  dim3 block(rm::kTX * rm::kTY), grid((W + rm::kTX - 1) / rm::kTX, (y1 - y0 + rm::kTY - 1) / rm::kTY, planes);
-  switch (g_lut_variant[0]) {  // legacy row-major-table kernel (kept for A/B timing and as a second implementation)
-    case 4: lut_stage_kernel<1, 1, 4><<<grid, block, 0, (cudaStream_t)stream>>>(t, in, ia, H, W, y0, y1, feat); break;
-    case 11: lut_stage_kernel<1, 1, 11><<<grid, block, 0, (cudaStream_t)stream>>>(t, in, ia, H, W, y0, y1, feat); break;
-    case 12: lut_stage_kernel<1, 1, 12><<<grid, block, 0, (cudaStream_t)stream>>>(t, in, ia, H, W, y0, y1, feat); break;
-    default: lut_stage_kernel<1, 1, 3><<<grid, block, 0, (cudaStream_t)stream>>>(t, in, ia, H, W, y0, y1, feat);
+  const int v1 = g_dbg.lut_variant[0];
+#ifdef LERF_EXPERIMENTS
+  if (v1 >= 80)  // paired-window / cell-pair tables (lut_pw.cu)
+    return launch_stage_pw(L, 1, in, ia, planes, H, W, y0, y1, feat, v1 - 80, (cudaStream_t)stream);
+  if (v1 >= 1 && v1 < 20) {  // row-major-table kernel
+    rm::StageTables t;
+    for (int i = 0; i < 3; ++i) t.t[i] = L->s1[i];
+    for (int i = 3; i < 6; ++i) t.t[i] = nullptr;
+    dim3 block(rm::kTX * rm::kTY), grid((W + rm::kTX - 1) / rm::kTX, (y1 - y0 + rm::kTY - 1) / rm::kTY, planes);
+    switch (v1) {
+      case 4: lut_stage_kernel<1, 1, 4><<<grid, block, 0, (cudaStream_t)stream>>>(t, in, ia, H, W, y0, y1, feat); break;
+      case 11: lut_stage_kernel<1, 1, 11><<<grid, block, 0, (cudaStream_t)stream>>>(t, in, ia, H, W, y0, y1, feat); break;
+      case 12: lut_stage_kernel<1, 1, 12><<<grid, block, 0, (cudaStream_t)stream>>>(t, in, ia, H, W, y0, y1, feat); break;
+      default: lut_stage_kernel<1, 1, 3><<<grid, block, 0, (cudaStream_t)stream>>>(t, in, ia, H, W, y0, y1, feat);
+    }
+    LERF_LAUNCHED();
+    return LERF_OK;
   }
-  LERF_LAUNCHED();
-  return LERF_OK;
+#endif
+  // production: cell-packed tables (lut_cell.cu)
+  return launch_stage_cell(L, 1, in, ia, planes, H, W, y0, y1, feat, v1 >= 20 && v1 < 40 ? v1 - 20 : 0, (cudaStream_t)stream);
 }
 
 /* Testing / tuning hook: block-swizzle weights used by the NEXT lerf_luts_create (see lerf_b200.h). */
 void lerf_debug_cell_hash(int ha, int hb, int hc) {
-  g_cell_hash[0] = ha; g_cell_hash[1] = hb; g_cell_hash[2] = hc;
+  g_dbg.cell_hash[0] = ha; g_dbg.cell_hash[1] = hb; g_dbg.cell_hash[2] = hc;
 }
 
 /* Testing / tuning hook (see lerf_b200.h). */
 void lerf_debug_lut_variant(int stage, int variant) {
-  if (stage == 1 || stage == 2) g_lut_variant[stage - 1] = variant;
+  if (stage == 1 || stage == 2) g_dbg.lut_variant[stage - 1] = variant;
 }
 
 int lerf_lut_stage2(const lerf_luts_t* luts, const uint8_t* feat, int planes, int H, int W, int y0, int y1,
@@ -266,30 +290,40 @@ int lerf_lut_stage2(const lerf_luts_t* luts, const uint8_t* feat, int planes, in
   if (rc) return rc;
   if (planes == 0 || y0 == y1) return LERF_OK;
   const lerf_luts_impl* L = reinterpret_cast<const lerf_luts_impl*>(luts);
-  rm::StageTables t;
-  for (int i = 0; i < 6; ++i) t.t[i] = L->s2[i];
   InAddr ia{1, (long long)H * W, 0, W, 1};
-  if (g_lut_variant[1] >= 80 || (g_lut_variant[1] == 0 && L->oC2 == 3))  // production (LeRF-G): paired-window tables (lut_pw.cu)
-    return launch_stage_pw(L, 2, feat, ia, planes, H, W, y0, y1, codes, g_lut_variant[1] >= 80 ? g_lut_variant[1] - 80 : 0, (cudaStream_t)stream);
-  if (g_lut_variant[1] >= 60 && L->oC2 == 3)  // max-tap block tables (lut_mt.cuh), production until r2a
-    return launch_stage2_mt(L, feat, planes, H, W, y0, y1, codes, g_lut_variant[1] >= 60 ? g_lut_variant[1] - 60 : 10,  // 10: single-word taps, 5 blocks/SM
-                            (cudaStream_t)stream);
-  if (g_lut_variant[1] >= 40 && L->oC2 == 3)  // table-format mix (lut_mix.cuh)
-    return launch_stage2_mix(L, feat, planes, H, W, y0, y1, codes, g_lut_variant[1] - 40, (cudaStream_t)stream);
-  if (g_lut_variant[1] >= 20 || (g_lut_variant[1] == 0 && L->oC2 == 1))  // oC = 3 cells thrash L1/L2 (profiles/): stage 2 stays on the row-major tables by default
-    return launch_stage_cell(L, 2, feat, ia, planes, H, W, y0, y1, codes, g_lut_variant[1] >= 20 ? g_lut_variant[1] - 20 : 0,
-                             (cudaStream_t)stream);
-  dim3 block(rm::kTX * rm::kTY), grid((W + rm::kTX - 1) / rm::kTX, (y1 - y0 + rm::kTY - 1) / rm::kTY, planes);
-  if (L->oC2 == 3) {
-    switch (g_lut_variant[1]) {
-      case 3: lut_stage_kernel<2, 3, 3><<<grid, block, 0, (cudaStream_t)stream>>>(t, feat, ia, H, W, y0, y1, codes); break;
-      default: lut_stage_kernel<2, 3, 4><<<grid, block, 0, (cudaStream_t)stream>>>(t, feat, ia, H, W, y0, y1, codes);
+  const int v2 = g_dbg.lut_variant[1];
+  // production: paired-window tables (lut_pw.cu) for LeRF-G, the cell kernel for LeRF-L (oC = 1 cells are 16 bytes and hit L1).
+  // 20..39 selects the cell kernel and 80.. the window kernel for either model: each is the other's second implementation.
+  if ((v2 == 0 && L->oC2 == 3) || v2 >= 80)
+    return launch_stage_pw(L, 2, feat, ia, planes, H, W, y0, y1, codes, v2 >= 80 ? v2 - 80 : 0, (cudaStream_t)stream);
+#ifdef LERF_EXPERIMENTS
+  if (v2 >= 60 && L->oC2 == 3)  // max-tap block tables (lut_mt.cuh), production of r1
+    return launch_stage2_mt(L, feat, planes, H, W, y0, y1, codes, v2 - 60, (cudaStream_t)stream);
+  if (v2 >= 40 && L->oC2 == 3)  // table-format mix (lut_mix.cuh)
+    return launch_stage2_mix(L, feat, planes, H, W, y0, y1, codes, v2 - 40, (cudaStream_t)stream);
+  if (v2 >= 1 && v2 < 20) {  // row-major-table kernel
+    rm::StageTables t;
+    for (int i = 0; i < 6; ++i) t.t[i] = L->s2[i];
+    dim3 block(rm::kTX * rm::kTY), grid((W + rm::kTX - 1) / rm::kTX, (y1 - y0 + rm::kTY - 1) / rm::kTY, planes);
+    if (L->oC2 == 3) {
+      if (v2 == 3) lut_stage_kernel<2, 3, 3><<<grid, block, 0, (cudaStream_t)stream>>>(t, feat, ia, H, W, y0, y1, codes);
+      else lut_stage_kernel<2, 3, 4><<<grid, block, 0, (cudaStream_t)stream>>>(t, feat, ia, H, W, y0, y1, codes);
+    } else {
+      lut_stage_kernel<2, 1, 4><<<grid, block, 0, (cudaStream_t)stream>>>(t, feat, ia, H, W, y0, y1, codes);
     }
-  } else {
-    lut_stage_kernel<2, 1, 4><<<grid, block, 0, (cudaStream_t)stream>>>(t, feat, ia, H, W, y0, y1, codes);
+    LERF_LAUNCHED();
+    return LERF_OK;
   }
-  LERF_LAUNCHED();
-  return LERF_OK;
+#endif
+  return launch_stage_cell(L, 2, feat, ia, planes, H, W, y0, y1, codes, v2 >= 20 && v2 < 40 ? v2 - 20 : 0, (cudaStream_t)stream);
+}
+
+int lerf_build_has_experiments(void) {
+#ifdef LERF_EXPERIMENTS
+  return 1;
+#else
+  return 0;
+#endif
 }
 
 }  // extern "C"

@@ -5,8 +5,10 @@
 #include <vector>
 
 #include "lut_cell_body.cuh"
+#ifdef LERF_EXPERIMENTS
 #include "lut_mix.cuh"
 #include "lut_mt.cuh"
+#endif
 
 namespace lerf {
 
@@ -22,6 +24,7 @@ __global__ void __launch_bounds__(kTX* kTY, MINB)
   lut_stage_cell_body<STAGE, OC>(tabs, in, ia, H, W, y0, y1, out, blockIdx.x, blockIdx.y, blockIdx.z, tile);
 }
 
+#ifdef LERF_EXPERIMENTS
 template <unsigned MTMASK, int MINB>
 __global__ void __launch_bounds__(kTX* kTY, MINB)
     lut_stage2_mix_kernel(mix::MixTables t, const uint8_t* __restrict__ feat, int H, int W, int y0, int y1,
@@ -37,9 +40,11 @@ __global__ void __launch_bounds__(256, MINB)
   __shared__ PX tile[(8 * NJ + 2 * mt::kHalo) * mt::kPitch];
   mt::lut_stage2_mt_body<NJ, LD, TABMASK, PX>(t, feat, H, W, y0, y1, out, blockIdx.x, blockIdx.y, blockIdx.z, tile);
 }
+#endif
 
 }  // namespace
 
+#ifdef LERF_EXPERIMENTS
 // Stage 2, oC = 3, max-tap block tables (lut_mt.cuh).  variant: tile height / register budget.
 int launch_stage2_mt(const lerf_luts_impl* L, const uint8_t* feat, int planes, int H, int W, int y0, int y1, uint8_t* out,
                      int variant, cudaStream_t st) {
@@ -104,6 +109,8 @@ int launch_stage2_mix(const lerf_luts_impl* L, const uint8_t* feat, int planes, 
   return LERF_OK;
 }
 
+#endif  // LERF_EXPERIMENTS
+
 // Builds the cell-packed copies of the nine tables inside one device allocation (called by lerf_luts_create).
 int build_cell_tables(lerf_luts_impl* L, const int8_t* const host_tables[9]) {
   const int oC = L->oC2;
@@ -121,6 +128,7 @@ int build_cell_tables(lerf_luts_impl* L, const int8_t* const host_tables[9]) {
   e = cudaMemcpy(L->cell_block, host.data(), total, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return fail(LERF_ECUDA, "cell-packed LUT upload failed: %s", cudaGetErrorString(e));
   L->cell_block_bytes = total;
+#ifdef LERF_EXPERIMENTS
   if (oC == 3) {  // max-tap block tables for stage 2 (lut_mt.cuh)
     std::vector<uint8_t> mtab(mt::kTableBytes);
     e = cudaMalloc(&L->mt_block, 6 * mt::kTableBytes);
@@ -132,6 +140,7 @@ int build_cell_tables(lerf_luts_impl* L, const int8_t* const host_tables[9]) {
       L->mt2[i] = (const uint8_t*)L->mt_block + i * mt::kTableBytes;
     }
   }
+#endif
   for (int i = 0; i < 3; ++i) L->c1[i] = (const uint8_t*)L->cell_block + i * s1_bytes;
   for (int i = 0; i < 6; ++i) L->c2[i] = (const uint8_t*)L->cell_block + 3 * s1_bytes + i * s2_bytes;
   return LERF_OK;
@@ -143,7 +152,12 @@ int launch_stage_cell(const lerf_luts_impl* L, int stage, const uint8_t* in, con
   for (int i = 0; i < 6; ++i) t.t[i] = stage == 1 ? (i < 3 ? L->c1[i] : nullptr) : L->c2[i];
   t.h = cell::Hash{(uint32_t)L->cell_hash[0], (uint32_t)L->cell_hash[1], (uint32_t)L->cell_hash[2]};
   dim3 block(kTX * kTY), grid((W + kTX - 1) / kTX, (y1 - y0 + kTY - 1) / kTY, planes);
+  if (g_dbg.carveout >= 0) {  // A/B hook; production leaves the driver's choice (the smallest carve-out that fits the blocks)
+    cudaFuncSetAttribute(lut_stage_cell_kernel<1, 1, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, g_dbg.carveout);
+    cudaFuncSetAttribute(lut_stage_cell_kernel<2, 1, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, g_dbg.carveout);
+  }
 #define LERF_GO(S, O, B) lut_stage_cell_kernel<S, O, B><<<grid, block, 0, st>>>(t, in, ia, H, W, y0, y1, out)
+#ifdef LERF_EXPERIMENTS
   if (stage == 1) {
     switch (variant) {
       case 2: LERF_GO(1, 1, 2); break;
@@ -162,6 +176,12 @@ int launch_stage_cell(const lerf_luts_impl* L, int stage, const uint8_t* in, con
   } else {
     LERF_GO(2, 1, 4);
   }
+#else
+  (void)variant;
+  if (stage == 1) LERF_GO(1, 1, 6);
+  else if (L->oC2 == 3) LERF_GO(2, 3, 4);
+  else LERF_GO(2, 1, 4);
+#endif
 #undef LERF_GO
   LERF_LAUNCHED();
   return LERF_OK;

@@ -44,6 +44,7 @@ __global__ void pw_repack_kernel(const int8_t* __restrict__ T, int oC, int entry
   if (oC == 3) o[1] = s[1];
 }
 
+#ifdef LERF_EXPERIMENTS
 // cell-pair table of family f (oC = 1): block `cell` = [orientation 0: 16 corners][orientation 1: 16 corners], corner m of
 // the CANONICAL window at byte cell::corner_pos(m) of its half
 __global__ void cp_repack_kernel(const int8_t* __restrict__ T, int f, uint8_t* __restrict__ dst) {
@@ -61,6 +62,7 @@ __global__ void cp_repack_kernel(const int8_t* __restrict__ T, int f, uint8_t* _
   d[0] = reinterpret_cast<const uint4*>(blk)[0];
   d[1] = reinterpret_cast<const uint4*>(blk)[1];
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------------------------
 // packed accumulators: oC = 3 keeps (n0 + n1 * 65536, n2) -- every partial sum of the twelve |N| <= 2048 fits 16 bits
@@ -140,6 +142,7 @@ struct FmtPW {
   }
 };
 
+#ifdef LERF_EXPERIMENTS
 struct FmtCP {
   using Lookup = cell::Simplex;
   static constexpr int nq = 8;
@@ -156,6 +159,7 @@ struct FmtCP {
     o1.a = cell::blend(q[4], q[5], q[6], q[7], L);
   }
 };
+#endif
 
 __device__ __forceinline__ bool in_tile(int x, int y) { return (unsigned)x < (unsigned)kT && (unsigned)y < (unsigned)kT; }
 
@@ -293,24 +297,33 @@ constexpr size_t smem_bytes() { return (size_t)kRows * kPitch * 4 + (size_t)7 * 
 
 }  // namespace pwk
 
-// Builds the paired-window copies of the nine tables: 6 families per stage (stage 1: family f reads table f >> 1).
+// Builds the paired-window copies of the stage-2 tables (6 window families).  An experiments build adds the stage-1
+// copies (family f reads table f >> 1) and the cell-pair tables.
 int build_pw_tables(lerf_luts_impl* L) {
   const int oC = L->oC2;
   const size_t b1 = pw::table_bytes(1), b2 = pw::table_bytes(oC);
-  const size_t total = 6 * b1 + 6 * b2;
+#ifdef LERF_EXPERIMENTS
+  const size_t off2 = 6 * b1;
+#else
+  const size_t off2 = 0;
+#endif
+  const size_t total = off2 + 6 * b2;
   cudaError_t e = cudaMalloc(&L->pw_block, total);
   if (e != cudaSuccess) return fail(LERF_ENOMEM, "cudaMalloc(%zu) for the paired-window LUT block failed: %s", total, cudaGetErrorString(e));
   L->pw_block_bytes = total;
   dim3 grid(65536 / 256, 64);
   for (int f = 0; f < 6; ++f) {
-    uint8_t* d1 = (uint8_t*)L->pw_block + f * b1;
-    uint8_t* d2 = (uint8_t*)L->pw_block + 6 * b1 + f * b2;
-    pwk::pw_repack_kernel<<<grid, 256>>>(L->s1[f >> 1], 1, 1, f, d1);
+    uint8_t* d2 = (uint8_t*)L->pw_block + off2 + f * b2;
     // the row-major device copy of an oC = 3 table is padded to 4 bytes per entry
     pwk::pw_repack_kernel<<<grid, 256>>>((const int8_t*)L->s2[f], oC, oC == 3 ? 4 : 1, f, d2);
-    L->pw1[f] = d1;
     L->pw2[f] = d2;
+#ifdef LERF_EXPERIMENTS
+    uint8_t* d1 = (uint8_t*)L->pw_block + f * b1;
+    pwk::pw_repack_kernel<<<grid, 256>>>(L->s1[f >> 1], 1, 1, f, d1);
+    L->pw1[f] = d1;
+#endif
   }
+#ifdef LERF_EXPERIMENTS
   // cell-pair tables (oC = 1 only): stage 1 always, stage 2 for LeRF-L
   const size_t cpb = (size_t)65536 * 32;
   e = cudaMalloc(&L->cp_block, (oC == 1 ? 12 : 6) * cpb);
@@ -325,6 +338,7 @@ int build_pw_tables(lerf_luts_impl* L) {
       L->cp2[f] = d2;
     }
   }
+#endif
   e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return fail(LERF_ECUDA, "paired-window LUT repack failed: %s", cudaGetErrorString(e));
   return LERF_OK;
@@ -333,10 +347,6 @@ int build_pw_tables(lerf_luts_impl* L) {
 int launch_stage_pw(const lerf_luts_impl* L, int stage, const uint8_t* in, const InAddr& ia, int planes, int H, int W,
                     int y0, int y1, uint8_t* out, int variant, cudaStream_t st) {
   if (!L->pw_block) return fail(LERF_EUNSUPPORTED, "paired-window tables were not built for this LUT set");
-  const bool cp = variant >= 10;  // variants 10+: cell-pair format (oC = 1)
-  if (cp && stage == 2 && L->oC2 != 1) return fail(LERF_EUNSUPPORTED, "cell-pair tables exist for oC = 1 only");
-  pwk::Tables t;
-  for (int i = 0; i < 6; ++i) t.t[i] = cp ? (stage == 1 ? L->cp1[i] : L->cp2[i]) : (stage == 1 ? L->pw1[i] : L->pw2[i]);
   dim3 grid((W + pwk::kT - 1) / pwk::kT, (y1 - y0 + pwk::kT - 1) / pwk::kT, planes);
 #define LERF_GO(F, S, O, LD, B)                                                                                   \
   {                                                                                                               \
@@ -348,8 +358,13 @@ int launch_stage_pw(const lerf_luts_impl* L, int stage, const uint8_t* in, const
     }                                                                                                             \
     pwk::lut_stage_pw_kernel<F, S, O, LD, B><<<grid, 256, pwk::smem_bytes<O>(), st>>>(t, in, ia, H, W, y0, y1, out); \
   }
-  using pwk::FmtCP;
   using pwk::FmtPW;
+  pwk::Tables t;
+#ifdef LERF_EXPERIMENTS
+  using pwk::FmtCP;
+  const bool cp = variant >= 10;  // variants 10+: cell-pair format (oC = 1)
+  if (cp && stage == 2 && L->oC2 != 1) return fail(LERF_EUNSUPPORTED, "cell-pair tables exist for oC = 1 only");
+  for (int i = 0; i < 6; ++i) t.t[i] = cp ? (stage == 1 ? L->cp1[i] : L->cp2[i]) : (stage == 1 ? L->pw1[i] : L->pw2[i]);
   if (cp) {
     if (stage == 1) {
       switch (variant) {
@@ -383,6 +398,13 @@ int launch_stage_pw(const lerf_luts_impl* L, int stage, const uint8_t* in, const
       default: LERF_GO(FmtPW<1>, 2, 1, 1, 3)
     }
   }
+#else
+  (void)variant;
+  if (stage != 2) return fail(LERF_EUNSUPPORTED, "the window kernel serves stage 2 in this build");
+  for (int i = 0; i < 6; ++i) t.t[i] = L->pw2[i];
+  if (L->oC2 == 3) LERF_GO(FmtPW<3>, 2, 3, 1, 3)
+  else LERF_GO(FmtPW<1>, 2, 1, 1, 3)
+#endif
 #undef LERF_GO
   LERF_LAUNCHED();
   return LERF_OK;

@@ -12,6 +12,7 @@
 //
 // Every block is exactly one role and runs the same device body as the stand-alone kernels (lut_cell_body.cuh,
 // lut_mt.cuh, resample_int.cuh): the bytes produced are identical to the three-launch path.
+#ifdef LERF_EXPERIMENTS
 #include "lut_cell_body.cuh"
 #include "lut_mt.cuh"
 #include "resample_int.cuh"
@@ -102,9 +103,6 @@ __global__ void __launch_bounds__(256, MINB) sr_pipeline_kernel(const __grid_con
   }
 }
 
-int g_pipe_minb = 3;       // tuning hook
-int g_pipe_group = 0;      // planes per group, 0 = auto
-bool g_pipe_enabled = false;  // measured slower than the three plain launches: off unless asked for
 
 template <int S>
 int run_pipeline(const lerf_luts_impl* L, const lerf_sr_plan_impl* P, const uint8_t* in, int planes, const InAddr& ia,
@@ -115,7 +113,7 @@ int run_pipeline(const lerf_luts_impl* L, const lerf_sr_plan_impl* P, const uint
   const int c0 = clampr(P->h_left_y[oy0]), c1 = clampr(P->h_left_y[oy1 - 1] + 1);
   const int f0 = clampr(c0 - 3), f1 = clampr(c1 + 3);
   const int ly0 = P->h_left_y[oy0], ly1 = P->h_left_y[oy1 - 1];
-  int gsz = g_pipe_group > 0 ? g_pipe_group : (planes >= 12 ? ia.channels : 1);
+  int gsz = g_dbg.pipe_group > 0 ? g_dbg.pipe_group : (planes >= 12 ? ia.channels : 1);
   if (gsz > planes) gsz = planes;
   const int G = (planes + gsz - 1) / gsz;
 
@@ -147,8 +145,8 @@ int run_pipeline(const lerf_luts_impl* L, const lerf_sr_plan_impl* P, const uint
     if (N > 0x7fffffffull) return fail(LERF_EINVAL, "lerf_sr_fused: too many blocks in one pipeline launch");
 #define LERF_GO(F, B) sr_pipeline_kernel<S, F, B><<<(unsigned)N, 256, 0, st>>>(a)
 #define LERF_GOB(F)                 \
-  if (g_pipe_minb == 4) LERF_GO(F, 4); \
-  else if (g_pipe_minb == 2) LERF_GO(F, 2); \
+  if (g_dbg.pipe_minb == 4) LERF_GO(F, 4); \
+  else if (g_dbg.pipe_minb == 2) LERF_GO(F, 2); \
   else LERF_GO(F, 3)
     switch (fmt) {
       case LERF_OUT_F32: LERF_GOB(LERF_OUT_F32); break;
@@ -168,7 +166,7 @@ int run_pipeline(const lerf_luts_impl* L, const lerf_sr_plan_impl* P, const uint
 // Called by lerf_sr_fused.  Returns -1 when the pipeline does not apply (the caller then issues the three plain launches).
 int sr_pipeline(const lerf_luts_impl* L, int kind, const lerf_sr_plan_impl* P, const uint8_t* in, int planes, const InAddr& ia,
                 float max_sigma, int oy0, int oy1, uint8_t* feat, uint8_t* codes, void* out, int fmt, cudaStream_t st) {
-  if (!g_pipe_enabled || kind != LERF_KIND_GAUSS || L->oC2 != 3 || !L->mt2[0] || !P->int_scale || planes < 2) return -1;
+  if (!g_dbg.pipe_enabled || kind != LERF_KIND_GAUSS || L->oC2 != 3 || !L->mt2[0] || !P->int_scale || planes < 2) return -1;
   if (!(max_sigma >= 0.0f) || max_sigma > 64.0f) return -1;
   if (fmt == LERF_OUT_F32 && ((uintptr_t)out & 15)) return -1;
   switch (P->int_scale) {
@@ -180,10 +178,15 @@ int sr_pipeline(const lerf_luts_impl* L, int kind, const lerf_sr_plan_impl* P, c
   }
 }
 
-void sr_pipeline_config(int enabled, int minb, int group_planes) {
-  g_pipe_enabled = enabled != 0;
-  g_pipe_minb = minb;
-  g_pipe_group = group_planes;
-}
 
 }  // namespace lerf
+
+#else  // product build: the pipeline kernel is an experiment; lerf_sr_fused issues its three launches
+#include "common.cuh"
+namespace lerf {
+int sr_pipeline(const lerf_luts_impl*, int, const lerf_sr_plan_impl*, const uint8_t*, int, const InAddr&, float, int, int, uint8_t*,
+                uint8_t*, void*, int, cudaStream_t) {
+  return -1;
+}
+}  // namespace lerf
+#endif

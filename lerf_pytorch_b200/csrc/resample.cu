@@ -330,7 +330,6 @@ static int fill_geom(WarpGeom& g, int H, int W, int oH, int oW, const double min
 
 using namespace lerf;
 
-static int g_force_generic = 0;  // 0 = production; 1 = float64 parity kernels only; 2 = no cell-owner kernel (tile kernel for integer scales too)
 
 extern "C" {
 
@@ -392,9 +391,9 @@ void lerf_sr_plan_destroy(lerf_sr_plan_t* plan) {
   if (!plan) return;
   lerf_sr_plan_impl* P = reinterpret_cast<lerf_sr_plan_impl*>(plan);
   cudaSetDevice(P->device);
-  cudaFree(P->left_y); cudaFree(P->dist_y); cudaFree(P->left_x); cudaFree(P->dist_x); cudaFree(P->coef_dev);
+  cudaFree(P->left_y); cudaFree(P->dist_y); cudaFree(P->left_x); cudaFree(P->dist_x);
+  for (int i = 0; i < P->coef_n; ++i) cudaFree(P->coef_dev[i]);
   free(P->h_left_y);
-  free(P->coef_host);
   delete P;
 }
 
@@ -416,16 +415,16 @@ int lerf_resize_sr(int kind, const lerf_sr_plan_t* plan, const uint8_t* feat, co
   if (planes == 0 || oy0 == oy1) return LERF_OK;
   CodeSrc hyp{codes};
   if (kind == LERF_KIND_GAUSS) {
-    if (P->int_scale && g_force_generic == 0) {  // periodic geometry: cell-owner kernel (resample_int.cu)
+    if (P->int_scale && g_dbg.force_generic == 0) {  // periodic geometry: cell-owner kernel (resample_int.cu)
       rc = resize_sr_int_gauss(P, feat, codes, planes, channels, max_sigma, oy0, oy1, out, out_format, (cudaStream_t)stream);
       if (rc != -1) return rc;
     }
   }
-  if (kind == LERF_KIND_LINEAR && P->int_scale && g_force_generic == 0) {  // periodic geometry, LeRF-L (resample_int.cu)
+  if (kind == LERF_KIND_LINEAR && P->int_scale && g_dbg.force_generic == 0) {  // periodic geometry, LeRF-L (resample_int.cu)
     rc = resize_sr_int_linear(P, feat, codes, planes, channels, max_sigma, oy0, oy1, out, out_format, (cudaStream_t)stream);
     if (rc != -1) return rc;
   }
-  if (g_force_generic != 1) {  // any scale >= 1: tile kernel (resample_tile.cu); the float64 kernels below are the parity path
+  if (g_dbg.force_generic != 1) {  // any scale >= 1: tile kernel (resample_tile.cu); the float64 kernels below are the parity path
     rc = resize_sr_tile(kind, P, feat, codes, planes, channels, max_sigma, oy0, oy1, out, out_format, (cudaStream_t)stream);
     if (rc != -1) return rc;
   }
@@ -436,13 +435,16 @@ int lerf_resize_sr(int kind, const lerf_sr_plan_t* plan, const uint8_t* feat, co
 }
 
 /* Testing hook: route integer scales through the generic kernel too (parity tests compare both). */
-void lerf_debug_force_generic(int on) { g_force_generic = on; }
+void lerf_debug_force_generic(int on) { g_dbg.force_generic = on; }
 
 /* Testing hook: 0 = the fast warp kernel reads img/codes + tables, 1 (default) = per-sample records (resample_tile.cu). */
-void lerf_debug_warp_records(int on) { warp_fast_config(on); }
+void lerf_debug_warp_records(int on) { g_dbg.warp_records = on != 0; }
 
 /* Testing / tuning hook for the integer-scale kernel (see lerf_b200.h). */
-void lerf_debug_resize_variant(int variant) { resize_int_config(variant); }
+void lerf_debug_resize_variant(int variant) {  // 10: production arithmetic with the byte-store uint8 epilogue of r1
+  g_dbg.u8_staged = variant != 10;
+  g_dbg.resize_variant = variant == 10 ? 0 : variant;
+}
 
 int lerf_resize_sr_f32(int kind, const lerf_sr_plan_t* plan, const float* img, const float* h0, const float* h1,
                        const float* h2, int planes, float max_sigma, float* out, lerf_stream_t stream) {
@@ -469,7 +471,7 @@ int lerf_warp(int kind, const uint8_t* feat, const uint8_t* codes, int planes, i
   int rc = fill_geom(g, H, W, oH, oW, minv, pad0_y, pad0_x, mask_pad0_y, mask_pad0_x, mask_border);
   if (rc) return rc;
   if (oH == 0 || oW == 0) return LERF_OK;
-  if (g_force_generic != 1) {  // fast path (resample_tile.cu); the float64 kernel below is the parity path
+  if (g_dbg.force_generic != 1) {  // fast path (resample_tile.cu); the float64 kernel below is the parity path
     rc = warp_fast(kind, feat, codes, planes, channels, H, W, oH, oW, minv, pad0_y, pad0_x, mask_pad0_y, mask_pad0_x,
                    mask_border, max_sigma, out, out_format, mask, (cudaStream_t)stream);
     if (rc != -1) return rc;

@@ -1,33 +1,45 @@
 // Integer-scale LeRF-G SR resampler: plain launches.  Kernel body and design notes: resample_int.cuh.
 #include <math.h>
 
+#include <mutex>
+
 #include "resample_int.cuh"
 
 namespace lerf {
 
 using namespace rsi;
 
-// Device copy of the per-code tables for `max_sigma`, cached in the plan (a plan, like the reference's resizer objects,
-// is not thread-safe).  The upload is stream-ordered before the kernels that read it.
-const CoefTabs* rsi::plan_coef_tabs(const lerf_sr_plan_impl* P, float max_sigma, cudaStream_t st) {
+// Device copies of the per-code tables, one per max_sigma seen (at most kCoefSlots), owned by the plan.  A copy is
+// built and uploaded with a SYNCHRONOUS cudaMemcpy under a mutex the first time its sigma is asked for and never
+// written again, so any number of streams and threads can launch on one plan (the r1 version uploaded on the
+// calling stream only and overwrote the table when sigma changed).
+const CoefTabs* rsi::plan_coef_tabs(const lerf_sr_plan_impl* P, float max_sigma, cudaStream_t) {
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
   lerf_sr_plan_impl* M = const_cast<lerf_sr_plan_impl*>(P);
-  if (!M->coef_dev) {
-    if (cudaMalloc(&M->coef_dev, sizeof(CoefTabs)) != cudaSuccess) return nullptr;
-    M->coef_host = malloc(sizeof(CoefTabs));
-    M->coef_sigma = -1.0f;
+  for (int i = 0; i < M->coef_n; ++i)
+    if (M->coef_sigma[i] == max_sigma) return (const CoefTabs*)M->coef_dev[i];
+  if (M->coef_n >= lerf_sr_plan_impl::kCoefSlots) return nullptr;
+  CoefTabs* host = new CoefTabs;
+  make_coef_tabs(max_sigma, *host);
+  void* dev = nullptr;
+  bool ok = cudaMalloc(&dev, sizeof(CoefTabs)) == cudaSuccess &&
+            cudaMemcpy(dev, host, sizeof(CoefTabs), cudaMemcpyHostToDevice) == cudaSuccess;
+  delete host;
+  if (!ok) {
+    cudaFree(dev);
+    cudaGetLastError();
+    return nullptr;
   }
-  if (M->coef_sigma != max_sigma) {
-    make_coef_tabs(max_sigma, *(CoefTabs*)M->coef_host);
-    if (cudaMemcpyAsync(M->coef_dev, M->coef_host, sizeof(CoefTabs), cudaMemcpyHostToDevice, st) != cudaSuccess) return nullptr;
-    M->coef_sigma = max_sigma;
-  }
-  return (const CoefTabs*)M->coef_dev;
+  M->coef_dev[M->coef_n] = dev;
+  M->coef_sigma[M->coef_n] = max_sigma;
+  ++M->coef_n;
+  return (const CoefTabs*)dev;
 }
 
 // testing hook: 0 = production = ROWQ form (unsigned fixed point, row term hoisted; resample_int.cuh), 4 blocks/SM;
 // 4 = ROWQ, 5 blocks/SM; 5 = plain form (4 FP64 per exponent), 5 blocks/SM (production until r1d); 2 = plain, 4 blocks/SM;
 // 1 = fully hoisted signed form, 3 blocks/SM
-int g_variant = 0;
 
 template <int S, int FMT, int MODE, int MINB>
 __global__ void __launch_bounds__(kCX* kCY, MINB)
@@ -59,20 +71,24 @@ __global__ void __launch_bounds__(kCX* kCY, 4)
   resize_int_u8_planar_body<S, CG>(feat, codes, H, W, oH, oW, g, ct, ly0, oy0, oy1, out, blockIdx.x, blockIdx.y, blockIdx.z, sm);
 }
 
-int g_u8_staged = 1;  // testing hook: 0 = the byte-store epilogue of r1
 
 template <int S>
 static int launch_int(const lerf_sr_plan_impl* P, const uint8_t* feat, const uint8_t* codes, int planes, int channels,
                       float max_sigma, int oy0, int oy1, void* out, int fmt, cudaStream_t st) {
-  const IntGeom<S> g = make_geom<S>(P, max_sigma, /*unsigned_form=*/g_variant == 0 || g_variant == 4 || g_variant == 11);
+#ifdef LERF_EXPERIMENTS
+  const int rv = g_dbg.resize_variant;
+#else
+  const int rv = g_dbg.resize_variant == 11 ? 11 : 0;  // 11: geometry from kernel parameters (the flavour of odd scales)
+#endif
+  const IntGeom<S> g = make_geom<S>(P, max_sigma, /*unsigned_form=*/rv == 0 || rv == 4 || rv == 11);
   const CoefTabs* ct = plan_coef_tabs(P, max_sigma, st);
   if (!ct) return fail(LERF_ECUDA, "uploading the hyper decode tables failed");
   // cell rows touched by the output band
   const int ly0 = P->h_left_y[oy0], ly1 = P->h_left_y[oy1 - 1];
   dim3 block(kCX * kCY), grid((P->W + 1 + kCX - 1) / kCX, (ly1 - ly0 + 1 + kCY - 1) / kCY, planes);
-  const bool cg = g_variant == 0 && geom_is_constexpr<S>(P);  // geometry factors as immediates (resample_int.cuh CGeom)
+  const bool cg = rv == 0 && geom_is_constexpr<S>(P);  // geometry factors as immediates (resample_int.cuh CGeom)
   // staged uint8 epilogue: the tile must fit the 48 KiB of static shared memory next to the coefficient tiles
-  if (g_u8_staged && (g_variant == 0 || g_variant == 11)) {
+  if (g_dbg.u8_staged && (rv == 0 || rv == 11)) {
     if constexpr (S == 4 || S == 8) {  // planar: aligned words through a lane shuffle (x4) or as they are (x8)
       if (fmt == LERF_OUT_U8 && g.ph_x == S / 2 && P->oW % 4 == 0 && ((uintptr_t)out & 3) == 0) {
         if (cg) resize_sr_int_gauss_u8p_kernel<S, true><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, ly0, oy0, oy1, (unsigned char*)out);
@@ -102,13 +118,19 @@ static int launch_int(const lerf_sr_plan_impl* P, const uint8_t* feat, const uin
 #define LERF_GK(F, HO, B)                                                                                              \
   resize_sr_int_gauss_kernel<S, F, HO, B><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, \
                                                                   channels, ly0, oy0, oy1, out)
-#define LERF_GO(F)                                   \
-  if (g_variant == 1) LERF_GK(F, 1, 3);              \
-  else if (g_variant == 2) LERF_GK(F, 0, 4);         \
-  else if (g_variant == 5) LERF_GK(F, 0, 5);         \
-  else if (g_variant == 4) LERF_GK(F, 2, 5);         \
-  else if (cg) LERF_GK(F, 3, 4);                     \
+#ifdef LERF_EXPERIMENTS
+#define LERF_GO(F)                                              \
+  if (g_dbg.resize_variant == 1) LERF_GK(F, 1, 3);              \
+  else if (g_dbg.resize_variant == 2) LERF_GK(F, 0, 4);         \
+  else if (g_dbg.resize_variant == 5) LERF_GK(F, 0, 5);         \
+  else if (g_dbg.resize_variant == 4) LERF_GK(F, 2, 5);         \
+  else if (cg) LERF_GK(F, 3, 4);                                \
   else LERF_GK(F, 2, 4)
+#else
+#define LERF_GO(F)               \
+  if (cg) LERF_GK(F, 3, 4);      \
+  else LERF_GK(F, 2, 4)
+#endif
   switch (fmt) {
     case LERF_OUT_F32: LERF_GO(LERF_OUT_F32); break;
     case LERF_OUT_U8: LERF_GO(LERF_OUT_U8); break;
@@ -135,10 +157,6 @@ int resize_sr_int_gauss(const lerf_sr_plan_impl* P, const uint8_t* feat, const u
   }
 }
 
-void resize_int_config(int variant) {  // 10: production arithmetic with the byte-store uint8 epilogue of r1; 11: geometry from kernel parameters (r1)
-  g_u8_staged = variant != 10;
-  g_variant = variant == 10 ? 0 : variant;
-}
 
 }  // namespace lerf
 

@@ -441,7 +441,6 @@ int resize_sr_tile(int kind, const lerf_sr_plan_impl* P, const uint8_t* feat, co
   return LERF_OK;
 }
 
-static bool g_warp_records = true;  // testing hook (lerf_debug_warp_records): false = table form of the fast kernel
 
 // Stream-ordered scratch for the records: a library-owned memory pool per device that keeps its memory between calls
 // (the default pool hands it back to the driver at every synchronisation: 6 ms per 100 MB call, measured).
@@ -482,13 +481,18 @@ int warp_fast(int kind, const uint8_t* feat, const uint8_t* codes, int planes, i
   dim3 block(32, 8), grid((oW + 31) / 32, (oH + 7) / 8, 1);
   // Gaussian: decode every input sample once into a 32-byte record (stream-ordered scratch), then gather records.
   TapRec* rec = nullptr;
-  if (kind == LERF_KIND_GAUSS && out && planes > 0 && g_warp_records) {
+  if (kind == LERF_KIND_GAUSS && out && planes > 0 && g_dbg.warp_records) {
     const long long n = (long long)planes * H * W;
     cudaMemPool_t pool = scratch_pool();
     if (pool && cudaMallocFromPoolAsync((void**)&rec, (size_t)n * sizeof(TapRec), pool, st) == cudaSuccess) {
       dim3 rgrid((unsigned)min((long long)((long long)H * W + 255) / 256, 4096LL), planes);
       warp_records_kernel<<<rgrid, 256, 0, st>>>(feat, codes, (long long)H * W, max_sigma, rec);
-      LERF_LAUNCHED();
+      ++g_launches;
+      const cudaError_t le = cudaGetLastError();
+      if (le != cudaSuccess) {  // give the scratch back before reporting
+        cudaFreeAsync(rec, st);
+        return fail(LERF_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(le), __FILE__, __LINE__);
+      }
     } else {
       (void)cudaGetLastError();  // no scratch: the table form below needs none
       rec = nullptr;
@@ -516,6 +520,5 @@ int warp_fast(int kind, const uint8_t* feat, const uint8_t* codes, int planes, i
   return LERF_OK;
 }
 
-void warp_fast_config(int use_records) { g_warp_records = use_records != 0; }
 
 }  // namespace lerf

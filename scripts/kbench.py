@@ -3,6 +3,8 @@
 import os
 import sys
 
+os.environ.setdefault("LERF_B200_EXPERIMENTS", "1")  # every tuning variant: liblerf_b200_exp.so
+
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -49,6 +51,11 @@ for kind in os.environ.get("KB_KINDS", "natural,uniform").split(","):
         assert v in (11, 12) or torch.equal(feat, ref_feat), "stage-1 variants disagree"
         print("%-8s stage1 %-24s %8.1f us/frame" % (kind, name, timeit(lambda: lp.lut_stage1(luts, frames, out=feat))), flush=True)
     L.lerf_debug_lut_variant(1, 0)
+    if ONLY != "prod":  # shared-memory carve-out of the production stage-1 kernel (percent of the unified L1 / shared memory)
+        for pct in (0, 7, 14, 28, 50):
+            L.lerf_debug_carveout(pct)
+            print("%-8s stage1 cell, carve-out %3d %%     %8.1f us/frame" % (kind, pct, timeit(lambda: lp.lut_stage1(luts, frames, out=feat))), flush=True)
+        L.lerf_debug_carveout(-1)
     codes = lp.lut_stage2(luts, ref_feat)
     s2_variants = ((0, "production (pw minb3)"), (70, "max-tap v10"), (1, "row-major minb4"), (23, "cell-48B minb3")) + tuple((60 + k, "max-tap v%d" % k) for k in range(13)) + ((42, "mix rm+max-tap 8/12"), (80, "pw minb3"), (81, "pw L1 minb3"), (82, "pw minb2"))
     if ONLY == "pw":
@@ -59,6 +66,12 @@ for kind in os.environ.get("KB_KINDS", "natural,uniform").split(","):
         assert torch.equal(c2, codes), "stage-2 variants disagree"
         print("%-8s stage2 %-24s %8.1f us/frame" % (kind, name, timeit(lambda: lp.lut_stage2(luts, ref_feat, out=c2))), flush=True)
     L.lerf_debug_lut_variant(2, 0)
+    if ONLY != "prod":  # access-policy window on the paired-window block instead of the cell block
+        for which, name in ((1, "window on pw block"), (0, "window on cell block")):
+            L.lerf_debug_l2_window(which)
+            luts._pinned_streams.clear()
+            luts.pin_l2()
+            print("%-8s stage2 production, %-20s %8.1f us/frame" % (kind, name, timeit(lambda: lp.lut_stage2(luts, ref_feat, out=c2))), flush=True)
     if ONLY != "prod":  # block-swizzle weights of the cell tables (baked in at LutSet creation)
         for hw in ():
             L.lerf_debug_cell_hash(*hw)

@@ -10,6 +10,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+os.environ.setdefault("LERF_B200_EXPERIMENTS", "1")
 import lerf_pytorch_b200 as lp  # noqa: E402
 import util  # noqa: E402
 

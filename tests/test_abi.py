@@ -17,8 +17,8 @@ def built():
     return lp
 
 
-def _declared_symbols():
-    src = open(os.path.join(ROOT, "include", "lerf_b200.h")).read()
+def _declared_symbols(header="lerf_b200.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(lerf_[a-z0-9_]+)\s*\(", src)))
 
@@ -32,6 +32,12 @@ def test_header_symbols_exported(built):
         assert hasattr(L, n), "liblerf_b200.so does not export %s" % n
         assert n in _lib.PROTOTYPES, "python binding lacks a prototype for %s" % n
     assert sorted(_lib.PROTOTYPES) == names
+    assert not [n for n in names if "debug" in n], "test hooks belong in lerf_b200_testing.h"
+    tnames = _declared_symbols("lerf_b200_testing.h")
+    for n in tnames:
+        assert hasattr(L, n), "liblerf_b200.so does not export %s" % n
+    assert sorted(_lib.TESTING_PROTOTYPES) == tnames
+    assert L.lerf_build_has_experiments() == 0, "the product library must be built without -DLERF_EXPERIMENTS"
 
 
 def test_abi_version_and_error_string(built):

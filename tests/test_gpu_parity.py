@@ -111,22 +111,34 @@ def test_stages_full_range_random_luts_vs_oracle(lp, orc, oC):
 
 @pytest.mark.parametrize("oC", [1, 3])
 def test_stage_kernel_variants_are_bitwise_identical(lp, oC):
-    """Two independent implementations (row-major-table kernel, cell-packed-table kernel and its tuning variants)
-    must produce the same bytes on full-range inputs and tables."""
+    """Independent implementations of the stages (cell-packed-table kernel, paired-window kernel, and in an experiments
+    build the row-major / mix / max-tap kernels and every tuning variant) must produce the same bytes on full-range
+    inputs and tables."""
     ld = random_luts(23 + oC, oC2=oC)
     ls = lp.LutSet(ld, linear=(oC == 1))
     img = _cuda(uniform_image(91, 75, 131))
     L = lp.lib()
+    # (stage-1 variant, stage-2 variant), include/lerf_b200_testing.h.  Product library: the cell kernel and the
+    # paired-window kernel are each other's second implementation for stage 2; a -DLERF_EXPERIMENTS build adds the
+    # row-major kernel (1), cell tuning variants (22..25), the table-format mix (40..), the max-tap kernel (60..), the
+    # stage-1 window kernels (80.., cell pairs 90..).
+    pairs = [(0, 0), (0, 24), (0, 80)]
+    if L.lerf_build_has_experiments():
+        pairs += [(1, 1), (22, 22), (23, 23), (25, 25), (80, 80), (81, 81), (90, 80), (91, 80), (92, 80)]
+        if oC == 3:
+            pairs += [(0, v) for v in (40, 42, 44, 60, 61, 62, 63, 67, 69, 70, 72, 81, 82)]
+        else:
+            pairs += [(0, 90), (0, 91)]
     try:
         ref = None
-        for v in (0, 1, 22, 23, 25) + ((40, 42, 44, 60, 61, 62, 63, 67, 69, 70, 72) if oC == 3 else ()):  # 40+: table-format mix (stage 2, oC = 3)
-            L.lerf_debug_lut_variant(1, v if v < 40 else 0)
-            L.lerf_debug_lut_variant(2, v)
+        for v1, v2 in pairs:
+            L.lerf_debug_lut_variant(1, v1)
+            L.lerf_debug_lut_variant(2, v2)
             feat = lp.lut_stage1(ls, img)
             codes = lp.lut_stage2(ls, feat)
             if ref is None:
                 ref = (feat.clone(), codes.clone())
-            assert torch.equal(feat, ref[0]) and torch.equal(codes, ref[1]), v
+            assert torch.equal(feat, ref[0]) and torch.equal(codes, ref[1]), (v1, v2)
     finally:
         L.lerf_debug_lut_variant(1, 0)
         L.lerf_debug_lut_variant(2, 0)
@@ -334,6 +346,8 @@ def test_pipeline_kernel_equals_three_launches(lp, luts, fmt):
     imgs = _cuda(np.stack([uniform_image(300 + i, 45, 83) for i in range(4)]))
     sr = lp.LerfSR(ls, 4)
     L = lp.lib()
+    if not L.lerf_build_has_experiments():
+        pytest.skip("the pipeline kernel is an experiment: run with LERF_B200_EXPERIMENTS=1 (liblerf_b200_exp.so)")
     try:
         L.lerf_debug_pipeline(0, 4, 0)
         ref = sr(imgs, out_format=fmt).clone()
@@ -356,11 +370,16 @@ def test_resize_kernel_variants_within_tolerance(lp, orc, luts):
     sr = lp.LerfSR(ls, 4)
     L = lp.lib()
     try:
-        for v in (0, 1, 2, 4, 5):
+        want = orc.to_uint8_hwc(ref)
+        for v in (0, 10, 11) + ((1, 2, 4, 5) if L.lerf_build_has_experiments() else ()):
             L.lerf_debug_resize_variant(v)
             out = sr(_cuda(img), out_format="f32").cpu().numpy().astype(np.float64)
             print("resize variant %d: max-abs err %.3g" % (v, _maxabs(out, ref)))
             assert _maxabs(out, ref) <= 1e-4, v  # north_star tolerance for fp32 output
+            for fmt in ("u8", "u8_hwc"):  # shuffle / staged-tile epilogues (0, 11) and the byte-store one (10)
+                u8 = sr(_cuda(img), out_format=fmt).cpu().numpy()
+                u8 = np.transpose(u8, (1, 2, 0)) if fmt == "u8" else u8
+                assert np.abs(u8.astype(int) - want.astype(int)).max() <= 1, (v, fmt)
     finally:
         L.lerf_debug_resize_variant(0)
 
