@@ -24,6 +24,15 @@ sys.path.insert(0, ROOT)
 H, W, C, SCALE = 1356, 2040, 3, 4  # cfg-3: DIV2K-sized 2040x1356 (WxH) frame, x4
 LUT_DIR = os.path.join(ROOT, "tests", "golden", "luts", "lerf-g")
 METRIC = "output MPix/s (LeRF-G x4 SR, 2040x1356 frames)"
+WORKLOAD = "cfg-3: LeRF-G LUT x4 SR of synthetic 2040x1356 frames, uint8 in -> float32 planar out"
+
+
+def config_block(frames, inp):
+    """The `config` of BOTH arms (ours and --impl reference): same workload, so the driver's same_config holds.  What an
+    arm actually ran per step (the reference arm times a bounded sample of it) is in its cpu_baseline.sample."""
+    return {"workload": WORKLOAD, "frames_per_gpu_per_step": frames, "input": inp, "sharding": "per image, no collective",
+            "l2": "each step writes %.2f GB per GPU (>> 126 MB L2) and alternates between two sets of input frames"
+                  % (frames * C * H * SCALE * W * SCALE * 4 / 1e9)}
 
 
 def measured_peak_gbs():
@@ -215,7 +224,7 @@ def host_threads():
 
 
 def cpu_port_rate(rows, seed, repeats=1, threads=None):
-    """Time the oracle C port (stage 1 + stage 2 + set_shape/resize + uint8 epilogue) on a `rows` x 2040 band of a
+    """Time the oracle C port (stage 1 + stage 2 + set_shape/resize, float64 out) on a `rows` x 2040 band of a
     cfg-3 frame.  Returns (out MPix/s, seconds per run, threads)."""
     from oracle import lerf_oracle as orc
     orc.build()
@@ -228,44 +237,91 @@ def cpu_port_rate(rows, seed, repeats=1, threads=None):
     for _ in range(repeats):
         t0 = time.perf_counter()
         out, _, _ = orc.lerf_sr(img, luts, SCALE, SCALE, linear=False)
-        orc.to_uint8_hwc(out)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     mpix = out.shape[1] * out.shape[2] / 1e6
     return mpix / best, best, nthreads
 
 
+def reference_rate(rows, workers, seed=3000, repeats=1):
+    """Time the UNMODIFIED reference (baseline/_ref, numpy, single-threaded by construction) on `workers` independent
+    `rows` x 2040 bands of cfg-3 frames, one process each.  Returns (out MPix/s, seconds, workers) or None if the
+    reference is not staged on this box."""
+    try:
+        from baseline import ref_runner as rr
+        if rr.load() is None:
+            return None
+        imgs = [natural_frame_numpy(seed + i, rows, W) for i in range(workers)]
+        secs, opix = rr.time_workers(imgs, LUT_DIR, SCALE, repeats)
+        return opix / 1e6 / secs, secs, workers
+    except Exception as ex:  # pragma: no cover
+        sys.stderr.write("reference_rate: %r\n" % (ex,))
+        return None
+
+
 def run_reference_arm(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores.  The real thing
+    (numpy, one process per host thread, each on its own band) when baseline/_ref is staged, the C/OpenMP oracle port
+    otherwise; the port is always timed beside it.  Each step is a bounded sample sized so the run ends in ~2.5 minutes."""
     if rank != 0:
         return 0
-    # bounded sample: calibrate on a 64-row band, then size the band so (steps + warmup) runs end in ~2.5 minutes
-    rate0, t0, nthreads = cpu_port_rate(64, 3000)
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    rows = int(max(32, min(H, 64 * budget / t0)))
-    if args.sample_rows > 0:
-        rows = int(min(H, args.sample_rows))
-    from oracle import lerf_oracle as orc
-    luts = orc.load_luts(LUT_DIR, linear=False)
-    img = natural_frame_numpy(3000, rows, W)
-    for _ in range(args.warmup):
-        out, _, _ = orc.lerf_sr(img, luts, SCALE, SCALE, linear=False)
-    t = time.perf_counter()
-    for _ in range(args.steps):
-        out, _, _ = orc.lerf_sr(img, luts, SCALE, SCALE, linear=False)
-        orc.to_uint8_hwc(out)
-    dt = (time.perf_counter() - t) / args.steps
-    mpix = out.shape[1] * out.shape[2] / 1e6
-    val = mpix / dt
-    sample = "per step: %dx%d band of a cfg-3 frame (x4 -> %.2f out MPix), natural-like seed 3000" % (rows, W, mpix)
+    nthr = host_threads()
+    steps_total = max(1, args.steps + args.warmup)
+    line_extra = {}
+    kind = "port"
+    ref = reference_rate(8, nthr)  # calibration: 8-row bands
+    if ref is not None:
+        kind = "reference"
+        budget = 110.0 / steps_total
+        rows = int(max(8, min(64, 8 * budget / ref[1])))
+        if args.sample_rows > 0:
+            rows = int(min(H, args.sample_rows))
+        from baseline import ref_runner as rr
+        imgs = [natural_frame_numpy(3000 + i, rows, W) for i in range(nthr)]
+        for _ in range(args.warmup):
+            rr.time_workers(imgs, LUT_DIR, SCALE)
+        t = time.perf_counter()
+        opix = 0
+        for _ in range(args.steps):
+            _, n = rr.time_workers(imgs, LUT_DIR, SCALE)
+            opix += n
+        dt = (time.perf_counter() - t) / args.steps
+        mpix = opix / args.steps / 1e6
+        val = mpix / dt
+        sample = ("per step: %d processes x one %dx%d band of a cfg-3 frame each (x4 -> %.2f out MPix in all), natural-like seeds "
+                  "3000.., through the reference's FourSimplexInterpFaster + SteeringGaussianResize2dNumpy (baseline/_ref)" % (nthr, rows, W, mpix))
+        prate, psecs, pthr = cpu_port_rate(H // 4, 3000)
+        line_extra["port"] = {"value": prate, "unit": "MPix/s", "cores": pthr, "kind": "port",
+                              "sample": "one %dx%d band (x4 -> %.1f out MPix) in %.2f s, oracle/lerf_oracle.c (OpenMP)" %
+                                        (H // 4, W, (H // 4) * SCALE * W * SCALE / 1e6, psecs)}
+        dtype = "f64 (numpy reference)"
+    else:
+        # bounded sample: calibrate on a 64-row band, then size the band so (steps + warmup) runs end in ~2.5 minutes
+        rate0, t0, nthr = cpu_port_rate(64, 3000)
+        budget = 150.0 / steps_total
+        rows = int(max(32, min(H, 64 * budget / t0)))
+        if args.sample_rows > 0:
+            rows = int(min(H, args.sample_rows))
+        from oracle import lerf_oracle as orc
+        luts = orc.load_luts(LUT_DIR, linear=False)
+        img = natural_frame_numpy(3000, rows, W)
+        for _ in range(args.warmup):
+            out, _, _ = orc.lerf_sr(img, luts, SCALE, SCALE, linear=False)
+        t = time.perf_counter()
+        for _ in range(args.steps):
+            out, _, _ = orc.lerf_sr(img, luts, SCALE, SCALE, linear=False)
+        dt = (time.perf_counter() - t) / args.steps
+        mpix = out.shape[1] * out.shape[2] / 1e6
+        val = mpix / dt
+        sample = "per step: %dx%d band of a cfg-3 frame (x4 -> %.2f out MPix), natural-like seed 3000, C/OpenMP oracle port" % (rows, W, mpix)
+        dtype = "f64 (CPU oracle port)"
+    cpu = {"value": val, "unit": "MPix/s", "cores": nthr, "kind": kind, "sample": sample}
+    cpu.update(line_extra)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "MPix/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64 (CPU oracle port)", "data": "synthetic",
-        "config": {"workload": "cfg-3: LeRF-G LUT x4 SR of synthetic 2040x1356 frames", "sample": sample},
-        "cpu_baseline": {"value": val, "unit": "MPix/s", "cores": nthreads, "kind": "port", "sample": sample,
-                         "note": "the reference is pure Python/numpy and cannot travel to the GPU box; this is the C oracle "
-                                 "port of its algorithm (oracle/lerf_oracle.c, OpenMP). The numpy reference itself measured "
-                                 "0.075 MPix/s on one core in the build container (BASELINE.md)."},
+        "dtype": dtype, "data": "synthetic", "config": config_block(args.frames, args.input),
+        "cpu_baseline": cpu,
         "e2e": {"value": val, "unit": "MPix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -275,6 +331,63 @@ def run_reference_arm(args, rank):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
+def rowband_arm(lp, luts, dev, rank, n_gpus, dist, torch, steps=5, warmup=3):
+    """BASELINE.json cfg-5: ONE synthetic 3840x2160 frame x8 -> 30720x17280; rank g computes the output rows of its band
+    from the whole input (the C ABI derives the input rows + 7-row halo the band needs; band edges sit on cell
+    boundaries).  No collective: the bands stay sharded.  Strong scaling: total work is fixed, value = the frame's
+    output MPix / max-over-ranks time.  Every rank also checks its band, bit for bit, against the same rows computed
+    from the input band + 7-row halo alone (what a rank would be sent)."""
+    global H, W
+    h5, w5, s5 = 2160, 3840, 8
+    saved = H, W
+    H, W = h5, w5
+    try:
+        frames = natural_frames_gpu(2, 5000, dev)  # the SAME two frames on every rank; steps alternate
+    finally:
+        H, W = saved
+    sr5 = lp.LerfSR(luts, s5)
+    oH5, oW5 = sr5.set_shape(h5, w5, C)
+    y0, y1 = lp.row_bands(oH5, n_gpus, align=s5)[rank]
+    out5 = torch.empty((1, C, oH5, oW5), dtype=torch.float32, device=dev)  # only rows [y0, y1) are ever written
+
+    def step(i):
+        sr5(frames[i % 2], out_format="f32", rows=(y0, y1), out=out5)
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        step(i)
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b) / steps], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    last = (steps - 1) % 2
+    r0, r1 = max(y0 // s5 - 7, 0), min((y1 + s5 - 1) // s5 + 7, h5)
+    crop = lp.LerfSR(luts, s5)(frames[last][r0:r1].contiguous(), out_format="f32")
+    ok = bool(torch.equal(crop[:, y0 - r0 * s5:y1 - r0 * s5], out5[0, :, y0:y1]))
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    if dist is not None:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    del out5, crop
+    torch.cuda.empty_cache()
+    mpix = oH5 * oW5 / 1e6
+    bytes_ = C * h5 * w5 + C * oH5 * oW5 * 4
+    peak, _ = measured_peak_gbs()
+    return {"workload": "cfg-5: LeRF-G x8 SR of one synthetic 3840x2160 frame -> 30720x17280, uint8 in -> float32 planar out, output "
+                        "row bands across the ranks (7-input-row halo), no collective",
+            "scaling": "strong", "n_gpus": n_gpus, "value": mpix / (ms * 1e-3), "unit": "MPix/s", "ms_per_frame": ms, "steps": steps,
+            "band_rows_per_rank": y1 - y0, "path_frac_per_gpu": bytes_ / n_gpus / (ms * 1e-3) / 1e9 / peak,
+            "band_equals_halo_crop_on_every_rank": bool(flag.item())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -285,6 +398,8 @@ def main():
     ap.add_argument("--input", default="natural", choices=["natural", "uniform"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-arms", action="store_true", help="skip the uniform-input, uint8 and cfg-5 row-band arms")
+    ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--sample-rows", type=int, default=0,
                     help="reference arm: rows of the frame band timed per step (0 = sized so the run ends in ~2.5 minutes)")
     args = ap.parse_args()
@@ -333,56 +448,64 @@ def main():
     out_mpix_step = B * oH * oW / 1e6
 
     names = ("lut_stage1", "lut_stage2", "resize_sr")
-    ev = []
 
-    def step(i, record=True):
-        frames = pool[(i % 2) * B:(i % 2 + 1) * B]
-        if record:
-            marks = [torch.cuda.Event(enable_timing=True)]
-            marks[0].record()
+    def timed_arm(frames2, fmt, out_buf, steps, warmup, record_kernels, sample_clocks=False):
+        """W warm-up steps, then K timed steps bracketed by barrier + synchronize; max over ranks.  Returns
+        (ms per step, per-kernel ms or None, launches, clocks or None)."""
+        ev = []
 
-            def rec(_name):
-                e = torch.cuda.Event(enable_timing=True)
-                e.record()
-                marks.append(e)
-            sr(frames, out_format="f32", out=out, record=rec)
-            ev.append(marks)
-        else:
-            sr(frames, out_format="f32", out=out)
+        def step(i, record):
+            frames = frames2[(i % 2) * B:(i % 2 + 1) * B]
+            if record:
+                marks = [torch.cuda.Event(enable_timing=True)]
+                marks[0].record()
 
-    for i in range(args.warmup):
-        step(i, record=False)
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    lp.lib().lerf_launch_count_reset()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        step(i)
-    e1.record()
-    torch.cuda.synchronize()
-    launches = int(lp.lib().lerf_launch_count())
-    if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    clk = clocks.stop()
-    ms_total = e0.elapsed_time(e1)
-    t_ms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_step = float(t_ms.item()) / args.steps
+                def rec(_name):
+                    e = torch.cuda.Event(enable_timing=True)
+                    e.record()
+                    marks.append(e)
+                sr(frames, out_format=fmt, out=out_buf, record=rec)
+                ev.append(marks)
+            else:
+                sr(frames, out_format=fmt, out=out_buf)
+
+        for i in range(warmup):
+            step(i, False)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = None
+        if sample_clocks:
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+        lp.lib().lerf_launch_count_reset()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(i, record_kernels)
+        e1.record()
+        torch.cuda.synchronize()
+        n_launch = int(lp.lib().lerf_launch_count())
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clk_ = sampler.stop() if sampler is not None else None
+        t_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        per_ = None
+        if record_kernels:
+            per_ = {n: 0.0 for n in names}
+            for marks in ev:
+                for k, n in enumerate(names):
+                    per_[n] += marks[k].elapsed_time(marks[k + 1])
+            per_ = {n: v / len(ev) for n, v in per_.items()}
+        return float(t_ms.item()) / steps, per_, n_launch, clk_
+
+    ms_step, per, launches, clk = timed_arm(pool, "f32", out, args.steps, args.warmup, True, sample_clocks=True)
     value = n_gpus * out_mpix_step / (ms_step * 1e-3)
 
-    # per-kernel device time over the timed region (CUDA events on the launching stream)
-    per = {n: 0.0 for n in names}
-    for marks in ev:
-        for k, n in enumerate(names):
-            per[n] += marks[k].elapsed_time(marks[k + 1])
-    per = {n: v / len(ev) for n, v in per.items()}
     top = max(per, key=per.get)
     P = B * C
     kbytes = {  # algorithmic bytes per launch (DESIGN.md "Kernels"): compulsory reads + writes of each kernel
@@ -417,6 +540,59 @@ def main():
         except Exception:
             pass
 
+    # the other input class of SURVEY.md 8d: uniform-random pixels (adversarial for the tables), same run, same kernels
+    other = None
+    if not args.no_extra_arms:
+        okind = "uniform" if args.input == "natural" else "natural"
+        opool = (uniform_frames_gpu if okind == "uniform" else natural_frames_gpu)(2 * B, 3000 + 1000 * rank, dev)
+        oms, oper, _, _ = timed_arm(opool, "f32", out, max(3, args.steps // 2), 3, True)
+        other = {"input": okind, "value": n_gpus * out_mpix_step / (oms * 1e-3), "unit": "MPix/s", "ms_per_step": oms,
+                 "kernel_ms": oper, "path_frac": path_bytes / (oms * 1e-3) / 1e9 / peak}
+        del opool
+    # secondary mode of SURVEY.md 8d: uint8 in -> uint8 out (the fused a10 epilogue; what run_host and the eval adapters use)
+    path_u8 = None
+    if not args.no_extra_arms:
+        path_u8 = {}
+        for fmt in ("u8", "u8_hwc"):
+            obuf = sr.alloc_out(B, C, fmt, dev)
+            ums, uper, _, _ = timed_arm(pool, fmt, obuf, max(3, args.steps // 2), 3, True)
+            ubytes = P * H * W * 1 + P * oH * oW * 1
+            path_u8[fmt] = {"bytes_per_step": ubytes, "ms_per_step": ums, "value": n_gpus * out_mpix_step / (ums * 1e-3),
+                            "achieved": ubytes / (ums * 1e-3) / 1e9, "frac": ubytes / (ums * 1e-3) / 1e9 / peak, "kernel_ms": uper}
+            del obuf
+        roofline["path_u8"] = path_u8
+        roofline["path_u8_note"] = ("3.19 B per output pixel (141.1 MB per frame): a quarter of the float32 path's bytes for the same "
+                                    "instruction-bound kernels, so the HBM fraction is about a quarter of path.frac by construction")
+
+    # what was timed is what the reference computes: one frame of the timed batch against the oracle, outside the timing
+    parity = None
+    if rank == 0 and not args.no_parity_check:
+        try:
+            from oracle import lerf_oracle as orc
+            orc.build()
+            orc.set_threads(host_threads())
+            fr = pool[:1]
+            got = sr(fr, out_format="f32")[0].cpu().numpy().astype(np.float64)
+            gfeat, gcodes = sr.stages(fr)
+            gu8 = sr(fr, out_format="u8_hwc")[0].cpu().numpy()
+            ref, rfeat, rcodes = orc.lerf_sr(fr[0].cpu().numpy(), orc.load_luts(LUT_DIR, linear=False), SCALE, SCALE, linear=False)
+            err = float(np.max(np.abs(got - ref)))
+            lsb = int(np.max(np.abs(gu8.astype(np.int32) - orc.to_uint8_hwc(ref).astype(np.int32))))
+            exact = bool(np.array_equal(gfeat.cpu().numpy(), rfeat) and np.array_equal(gcodes.cpu().numpy(), rcodes))
+            parity = {"checked": bool(exact and err <= 1e-4 and lsb <= 1), "frame": "frame 0 of the timed batch, %dx%d, all %d output samples" % (W, H, ref.size),
+                      "feat_codes_bit_exact": exact, "f32_max_abs_err": err, "f32_tolerance": 1e-4, "u8_max_lsb": lsb,
+                      "against": "oracle/lerf_oracle.c (float64), pinned to reference-generated goldens by tests/test_oracle_golden.py"}
+        except Exception as ex:  # pragma: no cover
+            parity = {"checked": False, "error": repr(ex)}
+
+    # cfg-5 (one 3840x2160 frame x8, output row bands across the ranks): the strong-scaling case of SURVEY.md 8e
+    rowband = None
+    if not args.no_extra_arms:
+        try:
+            rowband = rowband_arm(lp, luts, dev, rank, n_gpus, dist, torch)
+        except Exception as ex:  # pragma: no cover
+            rowband = {"value": None, "error": repr(ex)}
+
     # end to end through the public host API: pinned uint8 frames in, pinned uint8 HWC frames out, copies inside
     e2e = None
     try:
@@ -444,17 +620,25 @@ def main():
         dbuf = torch.empty((B, oH, oW, C), dtype=torch.uint8, device=dev)
         host_out.copy_(dbuf, non_blocking=True)
         torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()  # every rank copies at the same time: the ceiling of N ranks sharing the host, not of one alone
+        torch.cuda.synchronize()
         a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a2.record()
-        host_out.copy_(dbuf, non_blocking=True)
+        for _ in range(3):
+            host_out.copy_(dbuf, non_blocking=True)
         b2.record()
         torch.cuda.synchronize()
-        link_gbs = dbuf.numel() / (a2.elapsed_time(b2) * 1e-3) / 1e9
+        t3 = torch.tensor([a2.elapsed_time(b2) / 3], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        link_gbs = dbuf.numel() / (float(t3.item()) * 1e-3) / 1e9
         del dbuf
         e2e = {"value": n_gpus * out_mpix_step / (ms2 * 1e-3), "unit": "MPix/s", "h2d_bytes_per_step": B * H * W * C,
                "d2h_bytes_per_step": B * oH * oW * C, "ms_per_step": ms2, "steps": args.e2e_steps,
                "api": "LerfSR.run_host(pinned uint8 HWC in, pinned uint8 HWC out), 3 streams x 4 row bands per frame", "checksum": chk,
                "cpu_binding": cpu_binding, "d2h_link_GBps_plain_copy": link_gbs,
+               "d2h_link_note": "per rank, all ranks copying at once after a barrier (max over ranks)",
                "d2h_GBps_achieved": B * oH * oW * C / (ms2 * 1e-3) / 1e9}
     except Exception as ex:  # pragma: no cover
         e2e = {"value": None, "error": repr(ex)}
@@ -463,9 +647,17 @@ def main():
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
         try:
             rate, secs, nthreads = cpu_port_rate(H // 2, 3000)
-            cpu = {"value": rate, "unit": "MPix/s", "cores": nthreads, "kind": "port",
-                   "sample": "one %dx%d half frame of the same workload (x4 -> %.1f out MPix) in %.1f s" %
-                             (H // 2, W, (H // 2) * SCALE * W * SCALE / 1e6, secs)}
+            port = {"value": rate, "unit": "MPix/s", "cores": nthreads, "kind": "port",
+                    "sample": "one %dx%d half frame of the same workload (x4 -> %.1f out MPix) in %.1f s, oracle/lerf_oracle.c (OpenMP)" %
+                              (H // 2, W, (H // 2) * SCALE * W * SCALE / 1e6, secs)}
+            ref = reference_rate(24, host_threads())  # the unmodified reference (baseline/_ref), one process per host thread
+            if ref is not None:
+                cpu = {"value": ref[0], "unit": "MPix/s", "cores": ref[2], "kind": "reference",
+                       "sample": "%d processes x one 24x%d band of a cfg-3 frame each (x4 -> %.1f out MPix in all) in %.1f s, the "
+                                 "reference's own numpy functions (baseline/_ref)" % (ref[2], W, ref[2] * 24 * SCALE * W * SCALE / 1e6, ref[1]),
+                       "port": port}
+            else:
+                cpu = port
         except Exception as ex:  # pragma: no cover
             cpu = {"value": None, "error": repr(ex)}
 
@@ -475,11 +667,11 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32 LUT stages (dp4a on int8 tables); f64 exponent + f32 ex2/accumulate resampling",
             "data": "synthetic",
-            "config": {"workload": "cfg-3: LeRF-G LUT x4 SR of synthetic 2040x1356 frames, uint8 in -> float32 planar out",
-                       "frames_per_gpu_per_step": B, "input": args.input, "sharding": "per image, no collective",
-                       "l2": "each step writes %.2f GB per GPU (>> 126 MB L2) and alternates between two sets of input frames"
-                             % (B * C * oH * oW * 4 / 1e9)},
+            "config": config_block(B, args.input),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+            "parity_checked": bool(parity and parity.get("checked")), "parity": parity,
+            "value_uniform" if args.input == "natural" else "value_natural": other["value"] if other else None,
+            "other_input": other, "rowband_cfg5": rowband,
         }
         json_out.write(json.dumps(line) + "\n")
         json_out.flush()
