@@ -161,7 +161,8 @@ struct FmtCP {
 };
 #endif
 
-__device__ __forceinline__ bool in_tile(int x, int y) { return (unsigned)x < (unsigned)kT && (unsigned)y < (unsigned)kT; }
+template <int TY>
+__device__ __forceinline__ bool in_tile(int x, int y) { return (unsigned)x < (unsigned)kT && (unsigned)y < (unsigned)TY; }
 
 __device__ __forceinline__ int rhe_div(int num, int den) {  // round_half_even(num / den), num > 0, den even
   const int t = num + den / 2;
@@ -172,16 +173,16 @@ __device__ __forceinline__ int rhe_div(int num, int den) {  // round_half_even(n
 
 // Window group G (0 = 2x2 block, 1 = CH, 2 = CV, 3 = TD, 4 = TA): tap offsets in tile words, number of halo anchors and
 // their coordinates, destination of the far-end lookup.
-template <int G>
+template <int G, int TY>
 struct Grp {
   static constexpr int P = kPitch;
   static constexpr int o1 = G == 0 ? 1 : (G == 1 ? 1 : (G == 2 ? P : (G == 3 ? P + 1 : P - 1)));
   static constexpr int o2 = G == 0 ? P : 2 * o1, o3 = G == 0 ? P + 1 : 3 * o1;
-  static constexpr int nhalo = G == 0 ? 65 : (G == 1 || G == 2 ? 96 : 201);
+  static constexpr int nhalo = G == 0 ? TY + 33 : (G == 1 ? 3 * TY : (G == 2 ? 96 : 105 + 3 * TY));
   static constexpr int ddx = G == 0 ? 1 : (G == 1 ? 3 : (G == 2 ? 0 : (G == 3 ? 3 : -3)));
   static constexpr int ddy = G == 0 ? 1 : (G == 1 ? 0 : 3);
   __device__ static __forceinline__ void halo(int i, int& ax, int& ay) {
-    if (G == 0) { ax = i < 33 ? -1 : i - 33; ay = i < 33 ? i - 1 : -1; }              // column -1, then row -1
+    if (G == 0) { ax = i <= TY ? -1 : i - (TY + 1); ay = i <= TY ? i - 1 : -1; }      // column -1 (rows -1..TY-1), then row -1
     if (G == 1) { ax = -3 + i % 3; ay = i / 3; }                                     // columns -3..-1
     if (G == 2) { ax = i & 31; ay = -3 + (i >> 5); }                                 // rows -3..-1
     if (G == 3) { ax = i < 105 ? -3 + i % 35 : -3 + (i - 105) % 3; ay = i < 105 ? -3 + i / 35 : (i - 105) / 3; }
@@ -193,89 +194,91 @@ struct Grp {
 // table loads are issued before the first one is consumed (the kernel lives on load latency: ncu r2a, long_scoreboard).
 // Exchange arrays (each written exactly once per tile pixel, so plain stores and a single barrier before the final
 // sum):  X[0] S0.o1 (+1,+1)   X[1] S1.o0 (+1,0)   X[2] S1.o1 (0,+1)   X[3] CH (+3,0)   X[4] CV (0,+3)   X[5] TD (+3,+3)   X[6] TA (-3,+3)
-template <typename Fmt, int OC, int LD, int G>
+template <typename Fmt, int OC, int LD, int G, int NJ>
 __device__ __forceinline__ void group_pass(const Tables& t, const uint32_t* __restrict__ tile, Pk<OC>* __restrict__ X, int tx,
-                                           int tq, int tid, Pk<OC> own[4]) {
-  using Gr = Grp<G>;
+                                           int tq, int tid, Pk<OC> own[NJ]) {
+  constexpr int TY = 8 * NJ;
+  using Gr = Grp<G, TY>;
   constexpr int nq = Fmt::nq;
-  constexpr int kPx = kT * kT;
-  typename Fmt::Lookup L[5];
-  uint32_t q[5][nq];
+  constexpr int kPx = kT * TY;
+  typename Fmt::Lookup L[NJ + 1];
+  uint32_t q[NJ + 1][nq];
   int hx = 0, hy = 0;
   const bool h = tid < Gr::nhalo;
   if (h) Gr::halo(tid, hx, hy);
 #pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    if (j == 4 && !h) break;
-    const int ax = j < 4 ? tx : hx, ay = j < 4 ? tq + 8 * j : hy;
+  for (int j = 0; j <= NJ; ++j) {
+    if (j == NJ && !h) break;
+    const int ax = j < NJ ? tx : hx, ay = j < NJ ? tq + 8 * j : hy;
     const uint32_t* c = tile + (ay + kHalo) * kPitch + ax + kHalo;
     L[j] = Fmt::prepare(c[0], c[Gr::o1], c[Gr::o2], c[Gr::o3]);
     Fmt::template fetch<LD>(t.t[G == 0 ? 0 : G + 1], L[j], q[j]);
   }
 #pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    if (j == 4 && !h) break;
-    const int ax = j < 4 ? tx : hx, ay = j < 4 ? tq + 8 * j : hy;
+  for (int j = 0; j <= NJ; ++j) {
+    if (j == NJ && !h) break;
+    const int ax = j < NJ ? tx : hx, ay = j < NJ ? tq + 8 * j : hy;
     Pk<OC> f, r;
     Fmt::blend(q[j], L[j], f, r);
-    if (j < 4) own[j].add(f);
+    if (j < NJ) own[j].add(f);
     const int dx = ax + Gr::ddx, dy = ay + Gr::ddy;
-    if (in_tile(dx, dy)) X[(G == 0 ? 0 : G + 2) * kPx + dy * kT + dx] = r;
+    if (in_tile<TY>(dx, dy)) X[(G == 0 ? 0 : G + 2) * kPx + dy * kT + dx] = r;
   }
   if (G == 0) {  // the second table of the 2x2 block: rotation 1 lands on B (+1,0), rotation 3 on C (0,+1)
 #pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      if (j == 4 && !h) break;
+    for (int j = 0; j <= NJ; ++j) {
+      if (j == NJ && !h) break;
       Fmt::template fetch<LD>(t.t[1], L[j], q[j]);
     }
 #pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      if (j == 4 && !h) break;
-      const int ax = j < 4 ? tx : hx, ay = j < 4 ? tq + 8 * j : hy;
+    for (int j = 0; j <= NJ; ++j) {
+      if (j == NJ && !h) break;
+      const int ax = j < NJ ? tx : hx, ay = j < NJ ? tq + 8 * j : hy;
       Pk<OC> b0, b1;
       Fmt::blend(q[j], L[j], b0, b1);
-      if (in_tile(ax + 1, ay)) X[1 * kPx + ay * kT + ax + 1] = b0;
-      if (in_tile(ax, ay + 1)) X[2 * kPx + (ay + 1) * kT + ax] = b1;
+      if (in_tile<TY>(ax + 1, ay)) X[1 * kPx + ay * kT + ax + 1] = b0;
+      if (in_tile<TY>(ax, ay + 1)) X[2 * kPx + (ay + 1) * kT + ax] = b1;
     }
   }
 }
 
-template <typename Fmt, int STAGE, int OC, int LD, int MINB>
+template <typename Fmt, int STAGE, int OC, int LD, int MINB, int NJ = 4>
 __global__ void __launch_bounds__(256, MINB)
     lut_stage_pw_kernel(Tables t, const uint8_t* __restrict__ in, InAddr ia, int H, int W, int y0, int y1,
                         uint8_t* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int TY = 8 * NJ, kTileRows = TY + 2 * kHalo;
   uint32_t* tile = reinterpret_cast<uint32_t*>(smem_raw);
-  Pk<OC>* X = reinterpret_cast<Pk<OC>*>(smem_raw + kRows * kPitch * 4);
-  const int bx = blockIdx.x * kT, by = y0 + blockIdx.y * kT, p = blockIdx.z;
+  Pk<OC>* X = reinterpret_cast<Pk<OC>*>(smem_raw + kTileRows * kPitch * 4);
+  const int bx = blockIdx.x * kT, by = y0 + blockIdx.y * TY, p = blockIdx.z;
   const uint8_t* src = in + (long long)(p / ia.channels) * ia.batch_stride + (long long)(p % ia.channels) * ia.chan_stride;
   const int tid = threadIdx.x;
-  for (int i = tid; i < kRows * kRows; i += 256) {
+  for (int i = tid; i < kTileRows * kRows; i += 256) {
     const int r = i / kRows, c = i - r * kRows;
     const int gy = min(max(by + r - kHalo, 0), H - 1), gx = min(max(bx + c - kHalo, 0), W - 1);
     tile[r * kPitch + c] = cell::split_px(__ldcg(src + (long long)gy * ia.row_stride + (long long)gx * ia.pix_stride));
   }
   __syncthreads();
   const int tx = tid & 31, tq = tid >> 5;
-  Pk<OC> own[4];
+  Pk<OC> own[NJ];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) own[j].zero();
-  group_pass<Fmt, OC, LD, 0>(t, tile, X, tx, tq, tid, own);
-  group_pass<Fmt, OC, LD, 1>(t, tile, X, tx, tq, tid, own);
-  group_pass<Fmt, OC, LD, 2>(t, tile, X, tx, tq, tid, own);
-  group_pass<Fmt, OC, LD, 3>(t, tile, X, tx, tq, tid, own);
-  group_pass<Fmt, OC, LD, 4>(t, tile, X, tx, tq, tid, own);
+  for (int j = 0; j < NJ; ++j) own[j].zero();
+  group_pass<Fmt, OC, LD, 0, NJ>(t, tile, X, tx, tq, tid, own);
+  group_pass<Fmt, OC, LD, 1, NJ>(t, tile, X, tx, tq, tid, own);
+  group_pass<Fmt, OC, LD, 2, NJ>(t, tile, X, tx, tq, tid, own);
+  group_pass<Fmt, OC, LD, 3, NJ>(t, tile, X, tx, tq, tid, own);
+  group_pass<Fmt, OC, LD, 4, NJ>(t, tile, X, tx, tq, tid, own);
   __syncthreads();
 
   const int x = bx + tx;
   if (x >= W) return;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < NJ; ++j) {
     const int ty = tq + 8 * j, y = by + ty;
     if (y >= y1) continue;
     Pk<OC> s = own[j];
 #pragma unroll
-    for (int a = 0; a < 7; ++a) s.add(X[a * kT * kT + ty * kT + tx]);
+    for (int a = 0; a < 7; ++a) s.add(X[a * kT * TY + ty * kT + tx]);
     int n[3];
     s.get(n);
 #pragma unroll
@@ -292,8 +295,8 @@ __global__ void __launch_bounds__(256, MINB)
   }
 }
 
-template <int OC>
-constexpr size_t smem_bytes() { return (size_t)kRows * kPitch * 4 + (size_t)7 * kT * kT * sizeof(Pk<OC>); }
+template <int OC, int NJ = 4>
+constexpr size_t smem_bytes() { return (size_t)(8 * NJ + 2 * kHalo) * kPitch * 4 + (size_t)7 * kT * 8 * NJ * sizeof(Pk<OC>); }
 
 }  // namespace pwk
 
@@ -361,6 +364,11 @@ int launch_stage_pw(const lerf_luts_impl* L, int stage, const uint8_t* in, const
   using pwk::FmtPW;
   pwk::Tables t;
 #ifdef LERF_EXPERIMENTS
+  // (x) 32 x 8 tiles, one pixel per thread, for launches that do not fill the GPU (one 256 x 256 image is 192 blocks of
+  // 32 x 32): four times the blocks, but half again as many halo windows -- measured SLOWER on cfg-1 (21.7 vs 17.8 us).
+  dim3 grid_small((W + pwk::kT - 1) / pwk::kT, (y1 - y0 + 7) / 8, planes);
+#define LERF_GO_SMALL(F, O)                                                                                                  \
+  pwk::lut_stage_pw_kernel<F, 2, O, 1, 3, 1><<<grid_small, 256, pwk::smem_bytes<O, 1>(), st>>>(t, in, ia, H, W, y0, y1, out);
   using pwk::FmtCP;
   const bool cp = variant >= 10;  // variants 10+: cell-pair format (oC = 1)
   if (cp && stage == 2 && L->oC2 != 1) return fail(LERF_EUNSUPPORTED, "cell-pair tables exist for oC = 1 only");
@@ -390,6 +398,7 @@ int launch_stage_pw(const lerf_luts_impl* L, int stage, const uint8_t* in, const
     switch (variant) {
       case 1: LERF_GO(FmtPW<3>, 2, 3, 0, 3) break;
       case 2: LERF_GO(FmtPW<3>, 2, 3, 1, 2) break;
+      case 3: LERF_GO_SMALL(FmtPW<3>, 3) break;
       default: LERF_GO(FmtPW<3>, 2, 3, 1, 3)
     }
   } else {
@@ -406,6 +415,9 @@ int launch_stage_pw(const lerf_luts_impl* L, int stage, const uint8_t* in, const
   else LERF_GO(FmtPW<1>, 2, 1, 1, 3)
 #endif
 #undef LERF_GO
+#ifdef LERF_EXPERIMENTS
+#undef LERF_GO_SMALL
+#endif
   LERF_LAUNCHED();
   return LERF_OK;
 }

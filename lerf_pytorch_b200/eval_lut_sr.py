@@ -62,7 +62,17 @@ class Evaluator(object):
 
     def _worker(self, io, fname, img_lr, img_gt, scale_h, scale_w, result_path):
         opt, torch = self.opt, self.torch
-        sr = self.engine(scale_h, scale_w)
+        # eval_lut_sr.py:630-641: result paths of pre-upscaled inputs (RRDB x4, LUT x2, down2 / down4) resample by scale / post
+        post = 1
+        if "rrdb" in result_path:
+            post = 4
+        elif "lutx2" in result_path:
+            post = 2
+        elif "down2" in result_path:
+            post = 2
+        elif "down4" in result_path:
+            post = 4
+        sr = self.engine(scale_h / post, scale_w / post)
         gpu_score = None
         with torch.cuda.device(self.device):
             d_in = torch.from_numpy(np.ascontiguousarray(img_lr.astype(np.uint8))).to(self.device)

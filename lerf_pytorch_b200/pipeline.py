@@ -113,6 +113,14 @@ class LerfSR(object):
                                                 out.data_ptr(), _FMT[out_format], _stream_ptr(dev)))
         return out[0] if squeeze else out
 
+    def graphed(self, shape, out_format="f32", layout="HWC"):
+        """Small images (the Set5-sized inputs the reference's scripts actually run, cfg-1) are bound by launch latency:
+        three launches of a few microseconds of work each.  ``graphed`` captures them ONCE for an input ``shape`` into a
+        CUDA graph with static buffers and returns a callable ``g(img) -> out`` that copies ``img`` into the static input
+        and replays the graph (``g.input`` / ``g.output`` are the static tensors: fill ``g.input`` yourself and call
+        ``g.replay()`` to skip the copy).  Same kernels, same results."""
+        return GraphedSR(self, tuple(shape), out_format, layout)
+
     def run_host(self, host_in, host_out, depth=3, bands=4):
         """Host-to-host entry: ``host_in`` pinned uint8 [B,H,W,C], ``host_out`` pinned uint8 [B,oH,oW,C].
 
@@ -157,6 +165,41 @@ class LerfSR(object):
         return feat, lut_stage2(self.luts, feat)
 
 
+class GraphedSR(object):
+    """A captured ``LerfSR.__call__`` for one input shape (see ``LerfSR.graphed``)."""
+
+    def __init__(self, sr, shape, out_format, layout):
+        dev = sr.luts.device
+        self.input = torch.empty(shape, dtype=torch.uint8, device=dev)
+        batched = len(shape) == 4
+        x = self.input if batched else self.input.unsqueeze(0)
+        B, C = x.shape[0], (x.shape[3] if layout == "HWC" else x.shape[1])
+        H, W = (x.shape[1], x.shape[2]) if layout == "HWC" else (x.shape[2], x.shape[3])
+        sr.set_shape(H, W, C)
+        out = sr.alloc_out(B, C, out_format, dev)
+        self._slot = "graph%d" % id(self)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # warm-up outside the capture: plans, coefficient tables, function attributes
+            for _ in range(2):
+                sr(x, out_format=out_format, out=out, layout=layout, slot=self._slot)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            sr(x, out_format=out_format, out=out, layout=layout, slot=self._slot)
+        self.output = out if batched else out[0]
+        self._sr = sr  # keeps the scratch slot and the plan alive
+
+    def replay(self):
+        self.graph.replay()
+        return self.output
+
+    def __call__(self, img):
+        self.input.copy_(img, non_blocking=True)
+        return self.replay()
+
+
 class LerfWarp(object):
     """Homographic warping through the LUT path (one image per call, like the reference)."""
 
@@ -168,6 +211,34 @@ class LerfWarp(object):
             self.warper = AmplifiedLinearWarp2d()  # eval_lut_warp.py:38
         else:
             self.warper = SteeringGaussianWarp2d(support_sz=support_sz, max_sigma=max_sigma)
+
+    def batch(self, imgs, matrices, out_hw, out_format="f32", with_mask=True, out=None, masks=None):
+        """Several (image, homography) pairs of one input size onto one canvas size: ``imgs`` uint8 CUDA [B,H,W,C],
+        ``matrices`` B 3x3 arrays.  The LUT stages run ONCE over the whole batch (one launch each instead of B small
+        ones), the warps follow image by image into ``out`` ([B,C,oH,oW] float32 / uint8, or [B,oH,oW,C] for 'u8_hwc')
+        and ``masks`` ([B,oH,oW] uint8), allocated once here if not given.  Returns (out, masks)."""
+        if imgs.dtype != torch.uint8 or not imgs.is_cuda or imgs.dim() != 4:
+            raise ValueError("LerfWarp.batch needs a uint8 CUDA tensor [B,H,W,C]")
+        B, H, W, C = imgs.shape
+        oH, oW = int(out_hw[0]), int(out_hw[1])
+        dev = imgs.device
+        self.luts.pin_l2()
+        feat = lut_stage1(self.luts, imgs, "HWC")
+        codes = lut_stage2(self.luts, feat)
+        oC = self.luts.oC
+        if out is None:
+            if out_format == "u8_hwc":
+                out = torch.empty((B, oH, oW, C), dtype=torch.uint8, device=dev)
+            else:
+                out = torch.empty((B, C, oH, oW), dtype=torch.float32 if out_format == "f32" else torch.uint8, device=dev)
+        if with_mask and masks is None:
+            masks = torch.empty((B, oH, oW), dtype=torch.uint8, device=dev)
+        for b in range(B):
+            self.warper.set_shape([C, H, W], matrices[b], [C, oH, oW])
+            o = out[b:b + 1] if out_format == "u8_hwc" else out[b]
+            self.warper.warp_codes(feat[b * C:(b + 1) * C], codes[b * C * oC:(b + 1) * C * oC], channels=C, out_format=out_format,
+                                   with_mask=with_mask, mask_border=self.border, out=o, mask=masks[b] if with_mask else None)
+        return out, masks
 
     def __call__(self, img, matrix, out_hw, out_format="f32", with_mask=True):
         """img uint8 CUDA [H,W,C]; matrix 3x3 input->output; out_hw = (oH, oW) of the target canvas.

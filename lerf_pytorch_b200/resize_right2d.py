@@ -116,9 +116,11 @@ class Resize2d(object):
         self.out_shape = out_shape
         self.in_sz = [in_shape[1], in_shape[2]]
         self.out_sz = [out_shape[1], out_shape[2]]
-        if self.scale_factors[1] < 1.0 or self.scale_factors[2] < 1.0:
-            # :51-55 mutates support_sz for antialiasing; outside the LUT-inference configs
-            raise NotImplementedError("antialiased downscaling is not implemented")
+        if self.scale_factors[0] < 1.0 or self.scale_factors[1] < 1.0:
+            # The reference tests scale_factors[0] (the channel factor, always 1) and [1] (H) (:51): a HEIGHT factor below 1
+            # turns on its antialias branch (support_sz = ceil(supp / s_h) for good, :52-55), which is not implemented;
+            # a width factor below 1 alone does not and runs the plain 2x2 taps (float64 kernel), like the reference.
+            raise NotImplementedError("antialiased downscaling (height factor < 1) is not implemented")
         if self.support_sz != 2:
             raise NotImplementedError("support_sz=%r: only the default --suppSize 2 is implemented" % (self.support_sz,))
         ly, dy, pad_y = sr_axis_tables(self.in_sz[0], self.out_sz[0], self.scale_factors[1])
@@ -258,7 +260,7 @@ class Warp2d(object):
         if [H, W] != self.in_sz:
             raise ValueError("input is %dx%d but set_shape() was given %dx%d" % (H, W, self.in_sz[0], self.in_sz[1]))
 
-    def warp_codes(self, feat, codes, channels=3, out_format="f32", with_mask=False, mask_border=4, out=None):
+    def warp_codes(self, feat, codes, channels=3, out_format="f32", with_mask=False, mask_border=4, out=None, mask=None):
         """Fast path: feat uint8 [P,H,W] + codes uint8 [P*oC,H,W]; optionally also the validity mask of
         eval_lut_warp.py:197-204,229 (uint8 [oH,oW], 1 = valid)."""
         P, H, W = feat.shape
@@ -272,7 +274,8 @@ class Warp2d(object):
                 out = torch.empty((P, oH, oW), dtype=torch.uint8, device=dev)
             else:
                 out = torch.empty((P // channels, oH, oW, channels), dtype=torch.uint8, device=dev)
-        mask = torch.empty((oH, oW), dtype=torch.uint8, device=dev) if with_mask else None
+        if with_mask and mask is None:
+            mask = torch.empty((oH, oW), dtype=torch.uint8, device=dev)
         mp = _warp_pad0(self.minv, self.in_sz, 1) if with_mask else (0, 0)
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().lerf_warp(self.kind, feat.contiguous().data_ptr(), codes.contiguous().data_ptr(), P,

@@ -64,6 +64,13 @@ def cfg1():
     out = sr(img)
     ms = timeit(lambda: sr(img, out=out.unsqueeze(0)), 50)
     report("cfg-1", "LeRF-G x2 SR, one 256x256 image (3 launches, latency-bound)", ms, img.numel(), out.numel())
+    g = sr.graphed(img.shape)
+    g.input.copy_(img)
+    assert torch.equal(g.replay(), out)
+    ms = timeit(g.replay, 50)
+    report("cfg-1/graph", "the same three launches replayed from a CUDA graph (LerfSR.graphed)", ms, img.numel(), out.numel())
+    ms = timeit(lambda: g(img), 50)
+    report("cfg-1/graph+copy", "graph replay incl. the copy of the image into the graph's static input", ms, img.numel(), out.numel())
 
 
 def cfg2():
@@ -88,8 +95,9 @@ def cfg4():
     luts = lp.LutSet(lp.load_lut_dict(os.path.join(LUTS, "lerf-g")), device=dev)
     img = natural(1, 1024, 1024, 4000)[0]
     wp = lp.LerfWarp(luts)
+    mats = []
     for cls, lo, hi, canvas in (("isc", 2.0, 4.0, 3072), ("osc", 4.0, 9.5, 8192)):
-        tot, outs = 0.0, 0
+        tot, outs, Ms = 0.0, 0, []
         for k in range(8):  # 8 matrices per class from seed 4000+k
             rng = np.random.default_rng(4000 + k)
             a, d = rng.uniform(lo, hi, 2)
@@ -100,11 +108,20 @@ def cfg4():
             w = M @ corners
             w = w[:2] / w[2]
             M = np.array([[1, 0, canvas / 2 - w[0].mean()], [0, 1, canvas / 2 - w[1].mean()], [0, 0, 1.0]]) @ M
+            Ms.append(M)
             out, mask = wp(img, M, (canvas, canvas))
             tot += timeit(lambda: wp(img, M, (canvas, canvas)), 5)
             outs += out.numel()
         report("cfg-4/" + cls, "LeRF-G homographic warp 1024x1024 -> %dx%d canvas, mean of 8 random homographies "
                "(stages + mask + warp, output allocated per call)" % (canvas, canvas), tot / 8, img.numel(), outs // 8)
+        mats.append((cls, canvas, Ms))
+    for cls, canvas, Ms in mats:  # the 8 homographies as ONE batch: stages once over the batch, outputs allocated once
+        imgs = img.unsqueeze(0).expand(8, -1, -1, -1).contiguous()
+        out, masks = wp.batch(imgs, Ms, (canvas, canvas))
+        one, m1 = wp(img, Ms[3], (canvas, canvas))
+        assert torch.equal(torch.nan_to_num(out[3]), torch.nan_to_num(one)) and torch.equal(masks[3], m1)
+        ms = timeit(lambda: wp.batch(imgs, Ms, (canvas, canvas), out=out, masks=masks), 5)
+        report("cfg-4/" + cls + "/batch", "the same 8 warps as one LerfWarp.batch call (per image)", ms / 8, img.numel(), out.numel() // 8)
 
 
 def tile():

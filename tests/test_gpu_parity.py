@@ -810,3 +810,38 @@ def test_extreme_hypers_no_nan(lp):
             rs.set_shape([3, H, W], scale_factors=[s, s])
             out = rs.resize_codes(feat, codes)
             assert bool(torch.isfinite(out).all())
+
+
+def test_graph_replay_and_batched_warp_equal_plain_calls(lp, luts):
+    """LerfSR.graphed (the three launches of a small image replayed from a CUDA graph) and LerfWarp.batch (stages once over
+    a batch of images, outputs allocated once) are the same kernels on the same data: bitwise equal to the plain calls."""
+    _, ls = luts["g"]
+    img = _cuda(uniform_image(1234, 64, 80))
+    sr = lp.LerfSR(ls, 2)
+    for fmt in ("f32", "u8_hwc"):
+        want = sr(img, out_format=fmt).clone()
+        g = sr.graphed(img.shape, out_format=fmt)
+        assert torch.equal(g(img), want)
+        img2 = _cuda(uniform_image(77, 64, 80))
+        assert torch.equal(g(img2), sr(img2, out_format=fmt))       # replay on new data
+    wp = lp.LerfWarp(ls)
+    imgs = _cuda(np.stack([uniform_image(10 + i, 48, 56) for i in range(3)]))
+    Ms = [np.array([[2.0 + 0.3 * i, 0.1, 5.0], [-0.05, 2.2, 3.0 + i], [1e-4, -2e-4, 1.0]]) for i in range(3)]
+    out, masks = wp.batch(imgs, Ms, (120, 130))
+    for i in range(3):
+        o1, m1 = wp(imgs[i], Ms[i], (120, 130))
+        assert torch.equal(torch.nan_to_num(out[i]), torch.nan_to_num(o1)) and torch.equal(masks[i], m1), i
+
+
+@pytest.mark.parametrize("model,sh,sw", [("g", 1.0, 0.5), ("g", 2.0, 0.3), ("l", 1.5, 0.8)])
+def test_width_only_downscale_runs_like_the_reference(lp, orc, luts, model, sh, sw):
+    """resize_right2d_numpy.py:51 turns antialiasing on for a HEIGHT factor below 1 only; a width factor below 1 runs the
+    plain 2x2 taps (checked against the reference in the build container).  Height < 1 raises NotImplementedError."""
+    ld, ls = luts[model]
+    img = natural_image(8, 40, 52)
+    sr = lp.LerfSR(ls, sh, sw)
+    out = sr(_cuda(img), out_format="f32").cpu().numpy()
+    ref, _, _ = orc.lerf_sr(img, ld, sh, sw, linear=(model == "l"))
+    assert _maxabs(out, ref) <= FP32_TOL
+    with pytest.raises(NotImplementedError):
+        lp.LerfSR(ls, 0.75, 2.0).set_shape(40, 52)
