@@ -54,6 +54,78 @@ gb = host_out.numel() / 1e9
 rows = []
 ms = timed(lambda: (host_out.copy_(dbuf, non_blocking=True), torch.cuda.synchronize()), 3)
 rows.append(("plain pinned D2H copy, all ranks at once", ms, gb / (ms * 1e-3)))
+
+
+# r2: can the host side absorb more with another kind of pinned destination?
+def cudart():
+    import ctypes
+    import glob
+    cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "cuda_runtime", "lib", "libcudart.so*")) + ["libcudart.so.12", "libcudart.so"]
+    for c in cands:
+        try:
+            return ctypes.CDLL(c)
+        except OSError:
+            pass
+    return None
+
+
+def host_tensor(ptr, n):
+    import ctypes
+    return torch.frombuffer((ctypes.c_uint8 * n).from_address(ptr), dtype=torch.uint8)
+
+
+def try_variant(name, make):
+    try:
+        t, free = make()
+        ms_ = timed(lambda: (t.copy_(dbuf.view(-1), non_blocking=True), torch.cuda.synchronize()), 3)
+        rows.append((name, ms_, gb / (ms_ * 1e-3)))
+        free()
+    except Exception as ex:  # pragma: no cover
+        rows.append((name + " -- unavailable: %r" % (ex,), float("nan"), float("nan")))
+
+
+def make_wc():
+    import ctypes
+    rt = cudart()
+    p = ctypes.c_void_p()
+    rc = rt.cudaHostAlloc(ctypes.byref(p), ctypes.c_size_t(host_out.numel()), ctypes.c_uint(0x04))  # cudaHostAllocWriteCombined
+    if rc != 0:
+        raise RuntimeError("cudaHostAlloc(WriteCombined) -> %d" % rc)
+    return host_tensor(p.value, host_out.numel()), lambda: rt.cudaFreeHost(p)
+
+
+def make_huge(flags_huge):
+    import ctypes
+    import mmap
+    n = (host_out.numel() + (1 << 21) - 1) >> 21 << 21
+    fl = mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS | (getattr(mmap, "MAP_HUGETLB", 0x40000) if flags_huge else 0)
+    m = mmap.mmap(-1, n, flags=fl)
+    if not flags_huge:
+        m.madvise(getattr(mmap, "MADV_HUGEPAGE", 14))
+    buf = (ctypes.c_uint8 * n).from_buffer(m)
+    ptr = ctypes.addressof(buf)
+    ctypes.memset(ptr, 0, n)  # touch: the pages exist (and are huge where the kernel agrees) before they are registered
+    rt = cudart()
+    rc = rt.cudaHostRegister(ctypes.c_void_p(ptr), ctypes.c_size_t(n), ctypes.c_uint(0))
+    if rc != 0:
+        raise RuntimeError("cudaHostRegister -> %d" % rc)
+    t = torch.frombuffer(buf, dtype=torch.uint8)[:host_out.numel()]
+    return t, lambda: rt.cudaHostUnregister(ctypes.c_void_p(ptr))
+
+
+try_variant("  ... into cudaHostAlloc(WriteCombined)", make_wc)
+try_variant("  ... into MAP_HUGETLB + cudaHostRegister", lambda: make_huge(True))
+try_variant("  ... into THP (madvise) + cudaHostRegister", lambda: make_huge(False))
+# half of the ranks at a time: is the ceiling per box (shared) or per rank?
+if world > 1:
+    def halves():
+        for par in (0, 1):
+            if rank % 2 == par:
+                host_out.copy_(dbuf, non_blocking=True)
+            torch.cuda.synchronize()
+            dist.barrier()
+    ms = timed(halves, 3)
+    rows.append(("plain copy, even ranks then odd ranks", ms, gb / (ms * 1e-3)))
 for depth, bands in ((3, 4), (3, 1), (2, 4), (2, 1), (1, 1), (4, 8)):
     sr._slots = None
     ms = timed(lambda: sr.run_host(host_in, host_out, depth=depth, bands=bands), 3)
