@@ -178,6 +178,28 @@ int lerf_sr_fused(const lerf_luts_t* luts, int kind, const lerf_sr_plan_t* plan,
                   void* scratch, void* out, int out_format, lerf_stream_t stream);
 
 
+/* ---- LUT fine-tuning operators ---------------------------------------------------------------
+ * Forward and backward of the two differentiable pieces the reference trains through when it fine-tunes its LUTs
+ * (resample/train_model.py --lutft); float32 like its torch path.
+ *
+ * lerf_lut_ft_forward / _backward replace SWF2LUT.InterpTorchBatch (resample/model.py:172-385):
+ *   weight : DEVICE float32 [17^4][oC], the table in int8 units (the caller applies *127, the BPDA round and the clamp of
+ *            :177-179); img : DEVICE float32 [P][h+pad][w+pad], integer-valued 0..255, edge-padded by the mode's pad
+ *            (1 for s, 2 for d / y, 3 for c / t); out / grad_out : [P][oC][h][w] (already divided by q = 16).
+ *   grad_weight : [17^4][oC], ACCUMULATED into (zero it first); the pixels carry no gradient (floor_divide / %).
+ *   lsb_like_reference != 0 reproduces model.py:229-232,240-243, which reads the LSBs of modes c and t from the pixels
+ *   of mode y; 0 uses the mode's own taps like the inference path (eval_lut_sr.py:30-81).
+ * lerf_resize_sr_f32_backward is the gradient of lerf_resize_sr_f32 for LERF_KIND_GAUSS, i.e. of
+ * SteeringGaussianResize2dTorch.resize (resize_right/resize_right2d_torch.py:154-197): grad_img and grad_h0..2 are
+ * [P][H][W], ACCUMULATED into, and may be NULL where a gradient is not needed. */
+int lerf_lut_ft_forward(const float* weight, int oC, const float* img, int planes, int h, int w, char mode,
+                        int lsb_like_reference, float* out, lerf_stream_t stream);
+int lerf_lut_ft_backward(const float* grad_out, int oC, const float* img, int planes, int h, int w, char mode,
+                         int lsb_like_reference, float* grad_weight, lerf_stream_t stream);
+int lerf_resize_sr_f32_backward(int kind, const lerf_sr_plan_t* plan, const float* img, const float* h0, const float* h1,
+                                const float* h2, int planes, float max_sigma, const float* grad_out, float* grad_img,
+                                float* grad_h0, float* grad_h1, float* grad_h2, lerf_stream_t stream);
+
 /* Number of kernel launches issued by this library on the calling thread since the last reset
  * (bench.py reports it as gpu_launches). */
 long long lerf_launch_count(void);

@@ -193,6 +193,10 @@ class SteeringGaussianResize2d(Resize2d):
         self.max_sigma = max_sigma
 
     def resize(self, input, rho, sigma_x, sigma_y):
+        if torch.is_tensor(input) and input.dim() == 4 and torch.is_grad_enabled() and any(
+                torch.is_tensor(t) and t.requires_grad for t in (input, rho, sigma_x, sigma_y)):
+            from .lut_finetune import steering_gaussian_resize  # the differentiable torch flavour (fine-tuning, 8f item 4)
+            return steering_gaussian_resize(self, input, rho, sigma_x, sigma_y)
         return self._resize_f32(input, rho, sigma_x, sigma_y)
 
 
