@@ -2,6 +2,7 @@
 // over (sm_100a).  The distinct bytes touched stay at 32 MiB (L2-resident); only the number of 2 MiB pages grows.
 // Question (r2a): is the paired-window stage-2 kernel (6 tables x 24 planes of 2 MiB) held back by TLB misses?
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o build/tlbgather scripts/microbench/tlbgather.cu
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -30,10 +31,49 @@ __global__ void gather(const uint8_t* __restrict__ buf, uint32_t chunks, uint32_
   if (acc == 0x12345678u) *sink = acc;
 }
 
-int main() {
+// argv[1] = "vmm": back the span with ONE cuMemCreate allocation mapped at a 1 GiB-aligned address (does the driver then
+// use larger page-table entries than the 2 MiB of cudaMalloc?)
+static uint8_t* vmm_alloc(size_t bytes) {
+  typedef CUresult (*F_gran)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags);
+  typedef CUresult (*F_create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long);
+  typedef CUresult (*F_reserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long);
+  typedef CUresult (*F_map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long);
+  typedef CUresult (*F_access)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t);
+  F_gran gran; F_create create; F_reserve reserve; F_map map; F_access access;
+  cudaDriverEntryPointQueryResult qr;
+  if (cudaGetDriverEntryPoint("cuMemGetAllocationGranularity", (void**)&gran, cudaEnableDefault, &qr) != cudaSuccess) return nullptr;
+  cudaGetDriverEntryPoint("cuMemCreate", (void**)&create, cudaEnableDefault, &qr);
+  cudaGetDriverEntryPoint("cuMemAddressReserve", (void**)&reserve, cudaEnableDefault, &qr);
+  cudaGetDriverEntryPoint("cuMemMap", (void**)&map, cudaEnableDefault, &qr);
+  cudaGetDriverEntryPoint("cuMemSetAccess", (void**)&access, cudaEnableDefault, &qr);
+  CUmemAllocationProp prop = {};
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = 0;
+  size_t gmin = 0, grec = 0;
+  gran(&gmin, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM);
+  gran(&grec, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED);
+  printf("# vmm: granularity minimum %zu, recommended %zu bytes\n", gmin, grec);
+  CUmemGenericAllocationHandle h;
+  if (create(&h, bytes, &prop, 0) != CUDA_SUCCESS) return nullptr;
+  CUdeviceptr va = 0;
+  if (reserve(&va, bytes, 1ull << 30, 0, 0) != CUDA_SUCCESS) return nullptr;
+  if (map(va, bytes, 0, h, 0) != CUDA_SUCCESS) return nullptr;
+  CUmemAccessDesc ad = {};
+  ad.location = prop.location;
+  ad.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  if (access(va, bytes, &ad, 1) != CUDA_SUCCESS) return nullptr;
+  return (uint8_t*)va;
+}
+
+int main(int argc, char** argv) {
   const size_t span_max = 3072ull << 20;
   uint8_t* buf; uint32_t* sink;
-  if (cudaMalloc(&buf, span_max) != cudaSuccess) { printf("cudaMalloc failed\n"); return 1; }
+  cudaFree(0);
+  if (argc > 1) {
+    buf = vmm_alloc(span_max);
+    if (!buf) { printf("vmm allocation failed\n"); return 1; }
+  } else if (cudaMalloc(&buf, span_max) != cudaSuccess) { printf("cudaMalloc failed\n"); return 1; }
   cudaMalloc(&sink, 4);
   cudaMemset(buf, 1, span_max);
   int sms = 148;
