@@ -116,6 +116,20 @@ int lerf_lut_stage2(const lerf_luts_t* luts, const uint8_t* feat, int planes, in
 int lerf_sr_plan_create(int H, int W, int oH, int oW, const int32_t* left_y, const double* dist_y,
                         const int32_t* left_x, const double* dist_x, int device,
                         lerf_sr_plan_t** out);
+/* The same with the reference's NON-DEFAULT operator parameters: `support` taps per axis (the resizers' support_sz, any
+ * value >= 1; dist tables hold `support` entries per output: dist[support*o + k]; left may be any first-tap index), the
+ * np.pad mode of the IMAGE (pad_mode=..., :208; the hypers always replicate), and aa_scale = min_scale_factor when a height
+ * factor below 1 has turned antialiasing on (:51-55: the caller grows `support` to ceil(support / s); the Gaussian kind
+ * then scales its distances by aa_scale, :186-193), 1.0 otherwise.  Such a plan is served by the float64
+ * operation-order kernel only. */
+#define LERF_PAD_CONSTANT 0
+#define LERF_PAD_EDGE 1
+#define LERF_PAD_REFLECT 2
+#define LERF_PAD_SYMMETRIC 3
+#define LERF_PAD_WRAP 4
+int lerf_sr_plan_create_ex(int H, int W, int oH, int oW, int support, const int32_t* left_y, const double* dist_y,
+                           const int32_t* left_x, const double* dist_x, int pad_mode, double aa_scale, int device,
+                           lerf_sr_plan_t** out);
 void lerf_sr_plan_destroy(lerf_sr_plan_t* plan);
 
 /* ---- SR resampling ------------------------------------------------------------------------------

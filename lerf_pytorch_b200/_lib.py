@@ -30,6 +30,7 @@ PROTOTYPES = {
     "lerf_lut_stage1": (_c_i, [_c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_ll, _c_ll, _c_ll, _c_ll, _c_i, _c_i, _c_p, _c_p]),
     "lerf_lut_stage2": (_c_i, [_c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p, _c_p]),
     "lerf_sr_plan_create": (_c_i, [_c_i, _c_i, _c_i, _c_i, _c_p, _c_p, _c_p, _c_p, _c_i, _c_p]),
+    "lerf_sr_plan_create_ex": (_c_i, [_c_i, _c_i, _c_i, _c_i, _c_i, _c_p, _c_p, _c_p, _c_p, _c_i, ctypes.c_double, _c_i, _c_p]),
     "lerf_sr_plan_destroy": (None, [_c_p]),
     "lerf_resize_sr": (_c_i, [_c_i, _c_p, _c_p, _c_p, _c_i, _c_i, _c_f, _c_i, _c_i, _c_p, _c_i, _c_p]),
     "lerf_resize_sr_f32": (_c_i, [_c_i, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_f, _c_p, _c_p]),

@@ -103,6 +103,10 @@ struct lerf_sr_plan_impl {
   int int_scale;   // S if out = S*in on both axes with the periodic phase pattern, else 0
   int ph_y, ph_x;  // periodic geometry: the outputs whose first tap is l are S*l + ph + m, m = 0..S-1
   double ph_dist_y[8][2], ph_dist_x[8][2];  // their distances to tap 0 / tap 1
+  int general;     // lerf_sr_plan_create_ex: `support` taps per axis (dist tables hold `support` entries per output), np.pad mode
+  int support;     //   of the image and the antialias distance scale of the Gaussian kind; served by the float64 support kernel only
+  int pad_mode;
+  double aa_scale;
   int tile_ok;     // every 32 x 32 output group has its taps in a 33 x 33 input window (any scale >= 1), |dist| <= 1: resample_tile.cu
   int tile_rows;   // output rows per block of the tile kernel: the largest of 128, 96, 64, 32 whose taps fit 33 input rows
   static constexpr int kCoefSlots = 8;

@@ -29,7 +29,8 @@ int lerf_sr_fused(const lerf_luts_t* luts, int kind, const lerf_sr_plan_t* plan,
   const int H = P->H, W = P->W;
   // input rows the band depends on: taps -> +-3 rows of stage 2 -> +-3 rows of stage 1
   auto clampr = [&](int r) { return r < 0 ? 0 : (r > H - 1 ? H - 1 : r); };
-  const int c0 = clampr(P->h_left_y[oy0]), c1 = clampr(P->h_left_y[oy1 - 1] + 1);
+  const int supp = P->general ? P->support : 2;
+  const int c0 = clampr(P->h_left_y[oy0]), c1 = clampr(P->h_left_y[oy1 - 1] + supp - 1);
   const int f0 = clampr(c0 - 3), f1 = clampr(c1 + 3);
   uint8_t* feat = (uint8_t*)scratch;
   uint8_t* codes = feat + ((size_t)planes * H * W + 255) / 256 * 256;

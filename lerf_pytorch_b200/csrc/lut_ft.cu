@@ -202,6 +202,7 @@ int lerf_resize_sr_f32_backward(int kind, const lerf_sr_plan_t* plan, const floa
   if (kind != LERF_KIND_GAUSS) return fail(LERF_EUNSUPPORTED, "lerf_resize_sr_f32_backward: only LERF_KIND_GAUSS has a backward");
   if (!plan || !img || !h0 || !h1 || !h2 || !grad_out) return fail(LERF_EINVAL, "lerf_resize_sr_f32_backward: null pointer");
   const lerf_sr_plan_impl* P = reinterpret_cast<const lerf_sr_plan_impl*>(plan);
+  if (P->general) return fail(LERF_EUNSUPPORTED, "lerf_resize_sr_f32_backward: default operator parameters only (support 2, 'constant' pad)");
   if (planes < 0) return fail(LERF_EINVAL, "lerf_resize_sr_f32_backward: bad planes");
   if (planes == 0 || P->oH == 0 || P->oW == 0) return LERF_OK;
   if (planes > 65535) return fail(LERF_EINVAL, "lerf_resize_sr_f32_backward: more than 65535 planes");

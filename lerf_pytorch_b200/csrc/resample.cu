@@ -170,6 +170,101 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------------------
+// SR with the reference's NON-DEFAULT operator parameters (r2): any support size, np.pad mode of the image, and the
+// antialias scaling that a height factor below 1 turns on (resize_right2d_numpy.py:51-55, :186-193).  One thread = one
+// output sample, supp x supp taps, float64 in the reference's operation order (weights / sum first, then the products);
+// the Gaussian exponents are max-subtracted before exp (float64 exp: this is the parity path, not a fast one).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pad_src(int i, int n, int mode) {  // np.pad source index of UN-padded position i, -1 = constant 0
+  if (i >= 0 && i < n) return i;
+  switch (mode) {
+    case 0: return -1;
+    case 1: return i < 0 ? 0 : n - 1;
+    case 2: {
+      if (n == 1) return 0;
+      const int period = 2 * (n - 1);
+      i %= period;
+      if (i < 0) i += period;
+      return i < n ? i : period - i;
+    }
+    case 3: {
+      const int period = 2 * n;
+      i %= period;
+      if (i < 0) i += period;
+      return i < n ? i : period - 1 - i;
+    }
+    default: {
+      i %= n;
+      return i < 0 ? i + n : i;
+    }
+  }
+}
+
+template <int KIND, int FMT, typename ImgT, typename Hyp>
+__global__ void __launch_bounds__(256)
+    resize_sr_support_kernel(const ImgT* __restrict__ img, Hyp hyp, int H, int W, int oH, int oW, int supp,
+                             const int* __restrict__ left_y, const double* __restrict__ dist_y,
+                             const int* __restrict__ left_x, const double* __restrict__ dist_x, int pad_mode, double aa,
+                             int channels, float max_sigma, int oy0, int oy1, void* __restrict__ out) {
+  __shared__ HyperTab tab;
+  build_hyper_tab(tab, max_sigma, threadIdx.y * blockDim.x + threadIdx.x, blockDim.x * blockDim.y);
+  __syncthreads();
+  const int ox = blockIdx.x * blockDim.x + threadIdx.x;
+  const int oy = oy0 + blockIdx.y * blockDim.y + threadIdx.y;
+  const int p = blockIdx.z;
+  if (ox >= oW || oy >= oy1) return;
+  const long long plane_sz = (long long)H * W;
+  const int ly = left_y[oy], lx = left_x[ox];
+  const double* dr = dist_y + (long long)supp * oy;
+  const double* dc = dist_x + (long long)supp * ox;
+  // pass 1: the largest exponent (Gaussian) / the weight sum (linear); pass 2: weights / sum * value, in patch order a*supp+b
+  double m = -INFINITY, sum = 0.0;
+  for (int a = 0; a < supp; ++a)
+    for (int b = 0; b < supp; ++b) {
+      const int cy = clampi2(ly + b, 0, H - 1), cx = clampi2(lx + a, 0, W - 1);  // hypers: 'edge' (:172-174)
+      const long long off = (long long)cy * W + cx;
+      if (KIND == LERF_KIND_GAUSS) {
+        float rho, s_x, s_y;
+        hyp.gauss(tab, plane_sz, p, off, max_sigma, rho, s_x, s_y);
+        m = fmax(m, gauss_exponent(rho, s_x, s_y, aa * dr[b], aa * dc[a]));
+      } else {
+        const double al = (double)hyp.alpha(tab, plane_sz, p, off, max_sigma);
+        sum += lin_alpha(dr[b], al) * lin_alpha(dc[a], al);
+      }
+    }
+  if (KIND == LERF_KIND_GAUSS) {
+    for (int a = 0; a < supp; ++a)
+      for (int b = 0; b < supp; ++b) {
+        const int cy = clampi2(ly + b, 0, H - 1), cx = clampi2(lx + a, 0, W - 1);
+        float rho, s_x, s_y;
+        hyp.gauss(tab, plane_sz, p, (long long)cy * W + cx, max_sigma, rho, s_x, s_y);
+        sum += exp(gauss_exponent(rho, s_x, s_y, aa * dr[b], aa * dc[a]) - m);
+      }
+  }
+  double acc = 0.0;
+  for (int a = 0; a < supp; ++a)
+    for (int b = 0; b < supp; ++b) {
+      const int cy = clampi2(ly + b, 0, H - 1), cx = clampi2(lx + a, 0, W - 1);
+      const long long off = (long long)cy * W + cx;
+      double w;
+      if (KIND == LERF_KIND_GAUSS) {
+        float rho, s_x, s_y;
+        hyp.gauss(tab, plane_sz, p, off, max_sigma, rho, s_x, s_y);
+        w = exp(gauss_exponent(rho, s_x, s_y, aa * dr[b], aa * dc[a]) - m);
+      } else {
+        const double al = (double)hyp.alpha(tab, plane_sz, p, off, max_sigma);
+        w = lin_alpha(dr[b], al) * lin_alpha(dc[a], al);
+      }
+      const int iy = pad_src(ly + b, H, pad_mode), ix = pad_src(lx + a, W, pad_mode);  // image: np.pad(mode) (:208)
+      const double v = (iy >= 0 && ix >= 0) ? (double)load_img(img + (long long)p * plane_sz + (long long)iy * W + ix) : 0.0;
+      acc += v * (w / sum);  // 0/0 -> NaN exactly where numpy gives NaN
+    }
+  const long long ip = ((long long)p * oH + oy) * oW + ox;
+  const long long ih = (((long long)(p / channels) * oH + oy) * oW + ox) * channels + (p % channels);
+  store_sample<FMT>(out, 0, ip, ih, acc);
+}
+
+// ---------------------------------------------------------------------------------------------
 // homographic warp: one thread = one output pixel, all planes
 // ---------------------------------------------------------------------------------------------
 struct WarpGeom {
@@ -260,10 +355,15 @@ template <int KIND, typename ImgT, typename Hyp>
 static int launch_sr(const lerf_sr_plan_impl* P, const ImgT* img, Hyp hyp, int planes, int channels, float max_sigma,
                      int oy0, int oy1, void* out, int fmt, cudaStream_t st) {
   dim3 block(32, 8), grid((P->oW + 31) / 32, (oy1 - oy0 + 7) / 8, planes);
-#define LERF_GO(F)                                                                                         \
-  resize_sr_generic_kernel<KIND, F, ImgT, Hyp><<<grid, block, 0, st>>>(                                    \
-      img, hyp, P->H, P->W, P->oH, P->oW, P->left_y, P->dist_y, P->left_x, P->dist_x, channels, max_sigma, \
-      oy0, oy1, out)
+#define LERF_GO(F)                                                                                           \
+  if (P->general)                                                                                            \
+    resize_sr_support_kernel<KIND, F, ImgT, Hyp><<<grid, block, 0, st>>>(                                    \
+        img, hyp, P->H, P->W, P->oH, P->oW, P->support, P->left_y, P->dist_y, P->left_x, P->dist_x,          \
+        P->pad_mode, KIND == LERF_KIND_GAUSS ? P->aa_scale : 1.0, channels, max_sigma, oy0, oy1, out);       \
+  else                                                                                                       \
+    resize_sr_generic_kernel<KIND, F, ImgT, Hyp><<<grid, block, 0, st>>>(                                    \
+        img, hyp, P->H, P->W, P->oH, P->oW, P->left_y, P->dist_y, P->left_x, P->dist_x, channels, max_sigma, \
+        oy0, oy1, out)
   switch (fmt) {
     case LERF_OUT_F32: LERF_GO(LERF_OUT_F32); break;
     case LERF_OUT_U8: LERF_GO(LERF_OUT_U8); break;
@@ -387,6 +487,44 @@ int lerf_sr_plan_create(int H, int W, int oH, int oW, const int32_t* left_y, con
   return LERF_OK;
 }
 
+int lerf_sr_plan_create_ex(int H, int W, int oH, int oW, int support, const int32_t* left_y, const double* dist_y,
+                           const int32_t* left_x, const double* dist_x, int pad_mode, double aa_scale, int device,
+                           lerf_sr_plan_t** out) {
+  if (!left_y || !dist_y || !left_x || !dist_x || !out) return fail(LERF_EINVAL, "lerf_sr_plan_create_ex: null argument");
+  if (H < 1 || W < 1 || oH < 1 || oW < 1) return fail(LERF_EINVAL, "lerf_sr_plan_create_ex: bad sizes");
+  if (support < 1 || support > 64) return fail(LERF_EINVAL, "lerf_sr_plan_create_ex: support %d outside [1,64]", support);
+  if (pad_mode < LERF_PAD_CONSTANT || pad_mode > LERF_PAD_WRAP) return fail(LERF_EINVAL, "lerf_sr_plan_create_ex: unknown pad_mode %d", pad_mode);
+  if (!(aa_scale > 0.0)) return fail(LERF_EINVAL, "lerf_sr_plan_create_ex: aa_scale must be positive");
+  for (int o = 1; o < oH; ++o)
+    if (left_y[o] < left_y[o - 1]) return fail(LERF_EINVAL, "lerf_sr_plan_create_ex: left_y not monotone at %d", o);
+  for (int o = 1; o < oW; ++o)
+    if (left_x[o] < left_x[o - 1]) return fail(LERF_EINVAL, "lerf_sr_plan_create_ex: left_x not monotone at %d", o);
+  LERF_CUDA(cudaSetDevice(device));
+  lerf_sr_plan_impl* P = new lerf_sr_plan_impl();
+  memset(P, 0, sizeof(*P));
+  P->device = device; P->H = H; P->W = W; P->oH = oH; P->oW = oW;
+  P->general = 1; P->support = support; P->pad_mode = pad_mode; P->aa_scale = aa_scale;
+  cudaError_t e = cudaSuccess;
+  auto up = [&](void** d, const void* h, size_t n) {
+    if (e != cudaSuccess) return;
+    e = cudaMalloc(d, n);
+    if (e == cudaSuccess) e = cudaMemcpy(*d, h, n, cudaMemcpyHostToDevice);
+  };
+  up((void**)&P->left_y, left_y, sizeof(int) * oH);
+  up((void**)&P->dist_y, dist_y, sizeof(double) * support * oH);
+  up((void**)&P->left_x, left_x, sizeof(int) * oW);
+  up((void**)&P->dist_x, dist_x, sizeof(double) * support * oW);
+  if (e != cudaSuccess) {
+    lerf_sr_plan_destroy(reinterpret_cast<lerf_sr_plan_t*>(P));
+    return fail(LERF_ECUDA, "lerf_sr_plan_create_ex: upload failed: %s", cudaGetErrorString(e));
+  }
+  P->h_left_y = (int*)malloc(sizeof(int) * oH);
+  memcpy(P->h_left_y, left_y, sizeof(int) * oH);
+  P->tile_rows = 32;
+  *out = reinterpret_cast<lerf_sr_plan_t*>(P);
+  return LERF_OK;
+}
+
 void lerf_sr_plan_destroy(lerf_sr_plan_t* plan) {
   if (!plan) return;
   lerf_sr_plan_impl* P = reinterpret_cast<lerf_sr_plan_impl*>(plan);
@@ -414,6 +552,11 @@ int lerf_resize_sr(int kind, const lerf_sr_plan_t* plan, const uint8_t* feat, co
   if (rc) return rc;
   if (planes == 0 || oy0 == oy1) return LERF_OK;
   CodeSrc hyp{codes};
+  if (P->general) {  // non-default support / pad mode / antialias: the float64 support kernel
+    if (kind == LERF_KIND_GAUSS)
+      return launch_sr<LERF_KIND_GAUSS>(P, feat, hyp, planes, channels, max_sigma, oy0, oy1, out, out_format, (cudaStream_t)stream);
+    return launch_sr<LERF_KIND_LINEAR>(P, feat, hyp, planes, channels, max_sigma, oy0, oy1, out, out_format, (cudaStream_t)stream);
+  }
   if (kind == LERF_KIND_GAUSS) {
     if (P->int_scale && g_dbg.force_generic == 0) {  // periodic geometry: cell-owner kernel (resample_int.cu)
       rc = resize_sr_int_gauss(P, feat, codes, planes, channels, max_sigma, oy0, oy1, out, out_format, (cudaStream_t)stream);

@@ -51,11 +51,19 @@ def sr_axis_tables(in_sz, out_sz, scale, support_sz=2):
     return left.astype(np.int32), np.ascontiguousarray(dist, dtype=np.float64), (pad0, pad1)
 
 
+_PAD_MODES = {"constant": 0, "edge": 1, "reflect": 2, "symmetric": 3, "wrap": 4}  # np.pad modes of the IMAGE (LERF_PAD_*)
+
+
 class _Plan(object):
-    def __init__(self, H, W, oH, oW, ly, dy, lx, dx, device):
+    def __init__(self, H, W, oH, oW, ly, dy, lx, dx, device, support=2, pad_mode="constant", aa_scale=1.0):
         h = ctypes.c_void_p()
-        _lib.check(_lib.lib().lerf_sr_plan_create(H, W, oH, oW, ly.ctypes.data, dy.ctypes.data, lx.ctypes.data,
-                                                  dx.ctypes.data, device.index or 0, ctypes.byref(h)))
+        if support == 2 and pad_mode == "constant" and aa_scale == 1.0:  # what the eval scripts use: every fast path
+            _lib.check(_lib.lib().lerf_sr_plan_create(H, W, oH, oW, ly.ctypes.data, dy.ctypes.data, lx.ctypes.data,
+                                                      dx.ctypes.data, device.index or 0, ctypes.byref(h)))
+        else:  # non-default operator parameters: the float64 support kernel
+            _lib.check(_lib.lib().lerf_sr_plan_create_ex(H, W, oH, oW, int(support), ly.ctypes.data, dy.ctypes.data,
+                                                         lx.ctypes.data, dx.ctypes.data, _PAD_MODES[pad_mode],
+                                                         float(aa_scale), device.index or 0, ctypes.byref(h)))
         self.h = h
 
     def __del__(self):
@@ -82,8 +90,10 @@ class Resize2d(object):
     kind = None
 
     def __init__(self, support_sz=4, device="GPU", pad_mode="constant"):
-        if pad_mode != "constant":
-            raise NotImplementedError("only pad_mode='constant' (what the eval scripts use) is implemented")
+        if pad_mode not in _PAD_MODES:
+            raise NotImplementedError("pad_mode %r: np.pad modes %s are implemented" % (pad_mode, sorted(_PAD_MODES)))
+        if int(support_sz) < 1 or int(support_sz) > 64:
+            raise ValueError("support_sz must be in [1, 64]")
         self.eps = _EPS
         self.device = device
         self.support_sz = support_sz
@@ -116,15 +126,18 @@ class Resize2d(object):
         self.out_shape = out_shape
         self.in_sz = [in_shape[1], in_shape[2]]
         self.out_sz = [out_shape[1], out_shape[2]]
+        self._aa_scale = 1.0
         if self.scale_factors[0] < 1.0 or self.scale_factors[1] < 1.0:
-            # The reference tests scale_factors[0] (the channel factor, always 1) and [1] (H) (:51): a HEIGHT factor below 1
-            # turns on its antialias branch (support_sz = ceil(supp / s_h) for good, :52-55), which is not implemented;
-            # a width factor below 1 alone does not and runs the plain 2x2 taps (float64 kernel), like the reference.
-            raise NotImplementedError("antialiased downscaling (height factor < 1) is not implemented")
-        if self.support_sz != 2:
-            raise NotImplementedError("support_sz=%r: only the default --suppSize 2 is implemented" % (self.support_sz,))
-        ly, dy, pad_y = sr_axis_tables(self.in_sz[0], self.out_sz[0], self.scale_factors[1])
-        lx, dx, pad_x = sr_axis_tables(self.in_sz[1], self.out_sz[1], self.scale_factors[2])
+            # :51-55.  The reference tests scale_factors[0] (the channel factor, always 1) and [1] (H): a HEIGHT factor below
+            # 1 turns antialiasing on FOR GOOD and grows support_sz by 1 / s_h (it compounds over set_shape calls, like in
+            # the reference); a width factor below 1 alone does not.
+            self.antialias = True
+            self.min_scale_factor = min(self.scale_factors[1], self.scale_factors[0])
+            self.support_sz = ceil(self.support_sz / self.min_scale_factor)
+        if self.antialias and self.kind == LERF_KIND_GAUSS:
+            self._aa_scale = float(self.min_scale_factor)  # :186-193 (the amplified-linear resize() has no such branch)
+        ly, dy, pad_y = sr_axis_tables(self.in_sz[0], self.out_sz[0], self.scale_factors[1], self.support_sz)
+        lx, dx, pad_x = sr_axis_tables(self.in_sz[1], self.out_sz[1], self.scale_factors[2], self.support_sz)
         self.pad_vec = ((0, 0), pad_y, pad_x)  # :129
         self._tables = (ly, dy, lx, dx)
         self._plan = None
@@ -134,7 +147,8 @@ class Resize2d(object):
         if self._plan is None or self._plan_dev != device:
             ly, dy, lx, dx = self._tables
             with torch.cuda.device(device):
-                self._plan = _Plan(self.in_sz[0], self.in_sz[1], self.out_sz[0], self.out_sz[1], ly, dy, lx, dx, device)
+                self._plan = _Plan(self.in_sz[0], self.in_sz[1], self.out_sz[0], self.out_sz[1], ly, dy, lx, dx, device,
+                                   int(self.support_sz), self.pad_mode, self._aa_scale)
             self._plan_dev = device
         return self._plan.h
 
@@ -193,7 +207,8 @@ class SteeringGaussianResize2d(Resize2d):
         self.max_sigma = max_sigma
 
     def resize(self, input, rho, sigma_x, sigma_y):
-        if torch.is_tensor(input) and input.dim() == 4 and torch.is_grad_enabled() and any(
+        if torch.is_tensor(input) and input.dim() == 4 and int(self.support_sz) == 2 and self.pad_mode == "constant" and \
+                not self.antialias and torch.is_grad_enabled() and any(
                 torch.is_tensor(t) and t.requires_grad for t in (input, rho, sigma_x, sigma_y)):
             from .lut_finetune import steering_gaussian_resize  # the differentiable torch flavour (fine-tuning, 8f item 4)
             return steering_gaussian_resize(self, input, rho, sigma_x, sigma_y)

@@ -304,16 +304,47 @@ static int sr_axis(int in_sz, int out_sz, double scale, int supp, double* p, int
   return 0;
 }
 
+/* np.pad source index for padded position ip of an axis of length n padded by pad0 in front:
+ * mode 0 'constant' (-1 = outside), 1 'edge', 2 'reflect', 3 'symmetric', 4 'wrap' (numpy.pad semantics). */
+static int pad_src(int ip, int pad0, int n, int mode) {
+  int i = ip - pad0;
+  if (i >= 0 && i < n) return i;
+  switch (mode) {
+    case 0: return -1;
+    case 1: return i < 0 ? 0 : n - 1;
+    case 2: {
+      if (n == 1) return 0;
+      const int period = 2 * (n - 1);
+      i %= period;
+      if (i < 0) i += period;
+      return i < n ? i : period - i;
+    }
+    case 3: {
+      const int period = 2 * n;
+      i %= period;
+      if (i < 0) i += period;
+      return i < n ? i : period - 1 - i;
+    }
+    default: {
+      i %= n;
+      return i < 0 ? i + n : i;
+    }
+  }
+}
+
 /* SteeringGaussianResize2dNumpy.resize (:162-223) when kind == 0, with hypers
  * h0=rho, h1=sigma_x, h2=sigma_y in [0,1]; AmplifiedLinearResize2dNumpy.resize
- * (:243-282) when kind == 1, with h0 = alpha (h1, h2 ignored).  Support 2,
- * pad_mode 'constant' for the image, 'edge' for the hypers, no antialias.
+ * (:243-282) when kind == 1, with h0 = alpha (h1, h2 ignored).  Any support size (the
+ * caller applies the antialias growth of :51-55), np.pad mode `pad_mode` for the image, 'edge'
+ * for the hypers; aa_scale = min_scale_factor (:186-193: the Gaussian kind scales its
+ * distances by it when antialiasing; its weight factor cancels in the normalisation), 1 otherwise.
  *   img, h* : float32 [C][H][W];   out : double [C][oH][oW]
  * (oH, oW) = ceil(scale * in) is computed by the caller as at :41-45. */
-int lerf_oracle_resize_sr(int kind, const float* img, const float* h0, const float* h1,
-                          const float* h2, int C, int H, int W, double scale_h,
-                          double scale_w, int oH, int oW, float max_sigma, double* out) {
-  const int supp = 2;
+int lerf_oracle_resize_sr_ex(int kind, const float* img, const float* h0, const float* h1,
+                             const float* h2, int C, int H, int W, double scale_h,
+                             double scale_w, int oH, int oW, float max_sigma, int supp,
+                             int pad_mode, double aa_scale, double* out) {
+  if (supp < 1 || supp > 64) return 2;
   double* px = (double*)malloc(sizeof(double) * oH);
   double* py = (double*)malloc(sizeof(double) * oW);
   int* lx = (int*)malloc(sizeof(int) * oH);
@@ -322,15 +353,17 @@ int lerf_oracle_resize_sr(int kind, const float* img, const float* h0, const flo
   rc = sr_axis(H, oH, scale_h, supp, px, lx, &p0x, &p1x);
   if (!rc) rc = sr_axis(W, oW, scale_w, supp, py, ly, &p0y, &p1y);
   if (rc) { free(px); free(py); free(lx); free(ly); return rc; }
+  const int n = supp * supp;
 #pragma omp parallel for collapse(2) schedule(static)
   for (int c = 0; c < C; ++c) {
     for (int ox = 0; ox < oH; ++ox) {
       const size_t pl = (size_t)c * H * W;
+      double* wts = (double*)malloc(sizeof(double) * 2 * n);
+      double* nb = wts + n;
       for (int oy = 0; oy < oW; ++oy) {
-        double wts[4], nb[4];
-        /* flattened patch order a*2+b: row tap b, column tap a (np.meshgrid 'xy', :95-98) */
-        for (int a = 0; a < 2; ++a)
-          for (int b = 0; b < 2; ++b) {
+        /* flattened patch order a*supp+b: row tap b, column tap a (np.meshgrid 'xy', :95-98) */
+        for (int a = 0; a < supp; ++a)
+          for (int b = 0; b < supp; ++b) {
             const int fx = lx[ox] + b, fy = ly[oy] + a;       /* padded tap index */
             const double dx = px[ox] - (double)fx, dy = py[oy] - (double)fy; /* :131-134 */
             const int sx_ = fx - p0x, sy_ = fy - p0y;         /* un-padded source index */
@@ -338,23 +371,31 @@ int lerf_oracle_resize_sr(int kind, const float* img, const float* h0, const flo
             const size_t hi = pl + (size_t)cx * W + cy;
             double wgt;
             if (kind == 0)
-              wgt = sk_weight(dec_rho(h0[hi]), h1[hi] * max_sigma, h2[hi] * max_sigma, dx, dy);
+              wgt = sk_weight(dec_rho(h0[hi]), h1[hi] * max_sigma, h2[hi] * max_sigma, aa_scale * dx, aa_scale * dy);
             else
               wgt = linear_weight(max_sigma * dec_rho(h0[hi]), dx, dy);
-            wts[a * 2 + b] = wgt;
-            const int inside = (sx_ >= 0 && sx_ < H && sy_ >= 0 && sy_ < W);
-            nb[a * 2 + b] = inside ? (double)img[pl + (size_t)sx_ * W + sy_] : 0.0; /* 'constant', :208 */
+            wts[a * supp + b] = wgt;
+            const int ix = pad_src(fx, p0x, H, pad_mode), iy = pad_src(fy, p0y, W, pad_mode);
+            nb[a * supp + b] = (ix >= 0 && iy >= 0) ? (double)img[pl + (size_t)ix * W + iy] : 0.0; /* :208 */
           }
         double s = 0.0;
-        for (int k = 0; k < 4; ++k) s += wts[k];                 /* :205 */
+        for (int k = 0; k < n; ++k) s += wts[k];                 /* :205 */
         double acc = 0.0;
-        for (int k = 0; k < 4; ++k) acc += nb[k] * (wts[k] / s); /* :206, :220-221 */
+        for (int k = 0; k < n; ++k) acc += nb[k] * (wts[k] / s); /* :206, :220-221 */
         out[((size_t)c * oH + ox) * oW + oy] = acc;
       }
+      free(wts);
     }
   }
   free(px); free(py); free(lx); free(ly);
   return 0;
+}
+
+/* The default configuration of the eval scripts: support 2, 'constant' image pad, no antialias. */
+int lerf_oracle_resize_sr(int kind, const float* img, const float* h0, const float* h1,
+                          const float* h2, int C, int H, int W, double scale_h,
+                          double scale_w, int oH, int oW, float max_sigma, double* out) {
+  return lerf_oracle_resize_sr_ex(kind, img, h0, h1, h2, C, H, W, scale_h, scale_w, oH, oW, max_sigma, 2, 0, 1.0, out);
 }
 
 /* Warp2dNumpy.get_projected_grid2d (:306-342) for one output pixel: the inverse

@@ -90,7 +90,13 @@ def test_sr_set_shape_mirrors_reference_attributes(built):
     assert r.pad_vec == ((0, 0), (1, 1), (1, 1))
     r.set_shape([3, 20, 30], out_shape=[3, 40, 90])
     assert r.scale_factors == [1.0, 2.0, 3.0]
+    # a height factor below 1 latches antialiasing on and grows support_sz for good (resize_right2d_numpy.py:51-55)
+    r.set_shape([3, 20, 30], scale_factors=[0.5, 0.5])
+    assert r.antialias and r.support_sz == 4 and r.pad_vec == ((0, 0), (1, 1), (1, 1))
+    r.set_shape([3, 20, 30], scale_factors=[0.5, 0.5])
+    assert r.support_sz == 8  # it compounds, like in the reference
+    r4 = built.SteeringGaussianResize2dNumpy(support_sz=4, pad_mode="reflect")
+    r4.set_shape([3, 8, 8], scale_factors=[2, 2])
+    assert r4.pad_vec == ((0, 0), (2, 2), (2, 2)) and not r4.antialias
     with pytest.raises(NotImplementedError):
-        r.set_shape([3, 20, 30], scale_factors=[0.5, 0.5])
-    with pytest.raises(NotImplementedError):
-        built.SteeringGaussianResize2dNumpy(support_sz=4).set_shape([3, 8, 8], scale_factors=[2, 2])
+        built.SteeringGaussianResize2dNumpy(pad_mode="linear_ramp")

@@ -836,12 +836,51 @@ def test_graph_replay_and_batched_warp_equal_plain_calls(lp, luts):
 @pytest.mark.parametrize("model,sh,sw", [("g", 1.0, 0.5), ("g", 2.0, 0.3), ("l", 1.5, 0.8)])
 def test_width_only_downscale_runs_like_the_reference(lp, orc, luts, model, sh, sw):
     """resize_right2d_numpy.py:51 turns antialiasing on for a HEIGHT factor below 1 only; a width factor below 1 runs the
-    plain 2x2 taps (checked against the reference in the build container).  Height < 1 raises NotImplementedError."""
+    plain 2x2 taps (checked against the reference in the build container).  Height < 1: the antialias branch, through the
+    whole path."""
     ld, ls = luts[model]
     img = natural_image(8, 40, 52)
     sr = lp.LerfSR(ls, sh, sw)
     out = sr(_cuda(img), out_format="f32").cpu().numpy()
     ref, _, _ = orc.lerf_sr(img, ld, sh, sw, linear=(model == "l"))
     assert _maxabs(out, ref) <= FP32_TOL
-    with pytest.raises(NotImplementedError):
-        lp.LerfSR(ls, 0.75, 2.0).set_shape(40, 52)
+    aa = lp.LerfSR(ls, 0.75, 2.0)
+    out = aa(_cuda(img), out_format="f32").cpu().numpy()
+    assert aa.resizer.antialias and aa.resizer.support_sz == 3
+    ref, _, _ = orc.lerf_sr(img, ld, 0.75, 2.0, linear=(model == "l"))
+    assert _maxabs(out, ref) <= FP32_TOL
+
+
+def test_non_default_operator_parameters_vs_reference_goldens(lp, orc):
+    """support_sz 1 / 3 / 4 / 6, np.pad modes of the image, the antialias branch (height factor < 1): the float64 support
+    kernel against goldens generated by the reference (tests/golden/make_golden_general.py), float32-hyper API."""
+    G = golden("resize_general")
+    img, hy = G["img"], [G["h0"], G["h1"], G["h2"]]
+    for i, case in enumerate(G["cases"]):
+        supp, sh, sw, pm = str(case).split("|")
+        g = lp.SteeringGaussianResize2dNumpy(support_sz=int(supp), max_sigma=10, pad_mode=pm)
+        g.set_shape(list(img.shape), scale_factors=[float(sh), float(sw)])
+        assert g.support_sz == int(G["supp_after_%d" % i]), case
+        got = g.resize(img, *hy)
+        assert _maxabs(got, G["gauss_%d" % i]) <= FP32_TOL, case
+        lin = lp.AmplifiedLinearResize2dNumpy(support_sz=int(supp), pad_mode=pm)
+        lin.set_shape(list(img.shape), scale_factors=[float(sh), float(sw)])
+        assert _maxabs(lin.resize(img, hy[0]), G["linear_%d" % i]) <= FP32_TOL, case
+
+
+@pytest.mark.parametrize("supp,scale", [(4, 4), (4, 2.5), (3, 2)])
+def test_whole_path_with_support_4_vs_oracle(lp, orc, luts, supp, scale):
+    """--suppSize 4 through the whole LeRF-G path (uint8 codes, row bands, uint8 epilogue) against the oracle."""
+    ld, ls = luts["g"]
+    img = natural_image(44, 37, 45)
+    sr = lp.LerfSR(ls, scale, support_sz=supp)
+    out = sr(_cuda(img), out_format="f32")
+    ref, _, _ = orc.lerf_sr(img, ld, scale, scale, linear=False, supp=supp)
+    assert _maxabs(out.cpu().numpy(), ref) <= FP32_TOL
+    u8 = sr(_cuda(img), out_format="u8_hwc").cpu().numpy()
+    assert np.abs(u8.astype(int) - orc.to_uint8_hwc(ref).astype(int)).max() <= 1
+    oH = sr.out_sz[0]
+    band = torch.zeros_like(out)
+    for r0, r1 in ((0, 11), (11, oH // 2), (oH // 2, oH)):
+        sr(_cuda(img), out_format="f32", rows=(r0, r1), out=band.unsqueeze(0))
+    assert torch.equal(band, out)

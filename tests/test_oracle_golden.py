@@ -157,3 +157,24 @@ def test_whole_path_set5():
                                         tuple(int(v) for v in g["warp_gt_shape_" + tag]), linear=linear)
         assert np.array_equal(mask, g["warp_mask_" + tag]), tag
         assert _maxabs(out, g["warp_out_" + tag]) < 1e-8, tag
+
+
+def test_resize_non_default_parameters_match_reference_float64():
+    """Support sizes 1 / 3 / 4 / 6, np.pad modes of the image and the antialias branch of a height factor below 1
+    (resize_right2d_numpy.py:51-55, :186-193, :208): the oracle against goldens generated by the reference
+    (tests/golden/make_golden_general.py)."""
+    G = golden("resize_general")
+    img, hy = G["img"], [G["h0"], G["h1"], G["h2"]]
+    for i, case in enumerate(G["cases"]):
+        supp, sh, sw, pm = str(case).split("|")
+        g = orc.SteeringGaussianResize2dNumpy(support_sz=int(supp), max_sigma=10, pad_mode=pm)
+        g.set_shape(list(img.shape), scale_factors=[float(sh), float(sw)])
+        assert g.support_sz == int(G["supp_after_%d" % i]), case
+        ref = G["gauss_%d" % i]
+        assert np.max(np.abs(g.resize(img, *hy) - ref)) <= 1e-9, case
+        lin = orc.AmplifiedLinearResize2dNumpy(support_sz=int(supp), pad_mode=pm)
+        lin.set_shape(list(img.shape), scale_factors=[float(sh), float(sw)])
+        got, ref = lin.resize(img, hy[0]), G["linear_%d" % i]
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), case
+        m = np.isfinite(ref)
+        assert np.max(np.abs(got[m] - ref[m])) <= 1e-9, case
