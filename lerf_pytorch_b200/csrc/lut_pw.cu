@@ -90,6 +90,35 @@ struct Pk<1> {
   __device__ __forceinline__ void get(int* n) const { n[0] = a; }
 };
 
+// Exchange-array entry of the window kernel.  Pk<3> is 8 bytes; the compact form splits it into a 4-byte array (n0, n1 as
+// a packed int16 pair -- exactly Pk::a) and a 2-byte array (n2: one lookup's |N| <= 2048), 6 bytes per entry, so four
+// instead of three 32 x 32 blocks fit an SM's shared memory.
+template <int OC, bool X6>
+struct Xch {
+  Pk<OC>* p;
+  __device__ __forceinline__ void init(unsigned char* base, int entries) { p = reinterpret_cast<Pk<OC>*>(base); (void)entries; }
+  __device__ __forceinline__ void put(int i, const Pk<OC>& v) const { p[i] = v; }
+  __device__ __forceinline__ Pk<OC> get(int i) const { return p[i]; }
+  static constexpr int kBytes = sizeof(Pk<OC>);
+};
+template <>
+struct Xch<3, true> {
+  int* a;
+  short* b;
+  __device__ __forceinline__ void init(unsigned char* base, int entries) {
+    a = reinterpret_cast<int*>(base);
+    b = reinterpret_cast<short*>(base + (size_t)entries * 4);
+  }
+  __device__ __forceinline__ void put(int i, const Pk<3>& v) const { a[i] = v.a; b[i] = (short)v.b; }
+  __device__ __forceinline__ Pk<3> get(int i) const {
+    Pk<3> v;
+    v.a = a[i];
+    v.b = b[i];
+    return v;
+  }
+  static constexpr int kBytes = 6;
+};
+
 // LD: 0 = ld.global.nc (allocates in L1), 1 = nc + L1::no_allocate
 template <int LD>
 __device__ __forceinline__ void ld32(const uint8_t* p, uint32_t* q) {
@@ -194,8 +223,8 @@ struct Grp {
 // table loads are issued before the first one is consumed (the kernel lives on load latency: ncu r2a, long_scoreboard).
 // Exchange arrays (each written exactly once per tile pixel, so plain stores and a single barrier before the final
 // sum):  X[0] S0.o1 (+1,+1)   X[1] S1.o0 (+1,0)   X[2] S1.o1 (0,+1)   X[3] CH (+3,0)   X[4] CV (0,+3)   X[5] TD (+3,+3)   X[6] TA (-3,+3)
-template <typename Fmt, int OC, int LD, int G, int NJ>
-__device__ __forceinline__ void group_pass(const Tables& t, const uint32_t* __restrict__ tile, Pk<OC>* __restrict__ X, int tx,
+template <typename Fmt, int OC, int LD, int G, int NJ, typename XT>
+__device__ __forceinline__ void group_pass(const Tables& t, const uint32_t* __restrict__ tile, const XT& X, int tx,
                                            int tq, int tid, Pk<OC> own[NJ]) {
   constexpr int TY = 8 * NJ;
   using Gr = Grp<G, TY>;
@@ -222,7 +251,7 @@ __device__ __forceinline__ void group_pass(const Tables& t, const uint32_t* __re
     Fmt::blend(q[j], L[j], f, r);
     if (j < NJ) own[j].add(f);
     const int dx = ax + Gr::ddx, dy = ay + Gr::ddy;
-    if (in_tile<TY>(dx, dy)) X[(G == 0 ? 0 : G + 2) * kPx + dy * kT + dx] = r;
+    if (in_tile<TY>(dx, dy)) X.put((G == 0 ? 0 : G + 2) * kPx + dy * kT + dx, r);
   }
   if (G == 0) {  // the second table of the 2x2 block: rotation 1 lands on B (+1,0), rotation 3 on C (0,+1)
 #pragma unroll
@@ -236,20 +265,97 @@ __device__ __forceinline__ void group_pass(const Tables& t, const uint32_t* __re
       const int ax = j < NJ ? tx : hx, ay = j < NJ ? tq + 8 * j : hy;
       Pk<OC> b0, b1;
       Fmt::blend(q[j], L[j], b0, b1);
-      if (in_tile<TY>(ax + 1, ay)) X[1 * kPx + ay * kT + ax + 1] = b0;
-      if (in_tile<TY>(ax, ay + 1)) X[2 * kPx + (ay + 1) * kT + ax] = b1;
+      if (in_tile<TY>(ax + 1, ay)) X.put(1 * kPx + ay * kT + ax + 1, b0);
+      if (in_tile<TY>(ax, ay + 1)) X.put(2 * kPx + (ay + 1) * kT + ax, b1);
     }
   }
 }
 
-template <typename Fmt, int STAGE, int OC, int LD, int MINB, int NJ = 4>
+// Software-pipelined flavour of group_pass (r2): the loads of stage k+1 are ISSUED before the blocks of stage k are
+// consumed, so a warp always has a batch of table loads in flight while it blends the previous one.  Six stages: the 2x2
+// block on table 0, the same windows on table 1 (lookups reused), CH, CV, TD, TA.  Two register buffers of NJ + 1 blocks.
+template <typename Fmt, int NJ>
+struct StageBuf {
+  typename Fmt::Lookup L[NJ + 1];
+  uint32_t q[NJ + 1][Fmt::nq];
+  int hx, hy;
+  bool h;
+};
+
+// ST: 0 = S on table 0, 1 = S on table 1 (reuses `prev`'s lookups), 2..5 = groups 1..4
+template <typename Fmt, int LD, int ST, int NJ>
+__device__ __forceinline__ void stage_issue(const Tables& t, const uint32_t* __restrict__ tile, int tx, int tq, int tid,
+                                            StageBuf<Fmt, NJ>& b, const StageBuf<Fmt, NJ>* prev) {
+  constexpr int G = ST <= 1 ? 0 : ST - 1;
+  constexpr int TY = 8 * NJ;
+  using Gr = Grp<G, TY>;
+  b.h = tid < Gr::nhalo;
+  b.hx = b.hy = 0;
+  if (b.h) Gr::halo(tid, b.hx, b.hy);
+#pragma unroll
+  for (int j = 0; j <= NJ; ++j) {
+    if (j == NJ && !b.h) break;
+    if (ST == 1) {
+      b.L[j] = prev->L[j];
+    } else {
+      const int ax = j < NJ ? tx : b.hx, ay = j < NJ ? tq + 8 * j : b.hy;
+      const uint32_t* c = tile + (ay + kHalo) * kPitch + ax + kHalo;
+      b.L[j] = Fmt::prepare(c[0], c[Gr::o1], c[Gr::o2], c[Gr::o3]);
+    }
+    Fmt::template fetch<LD>(t.t[ST], b.L[j], b.q[j]);
+  }
+}
+
+template <typename Fmt, int OC, int ST, int NJ, typename XT>
+__device__ __forceinline__ void stage_consume(const StageBuf<Fmt, NJ>& b, const XT& X, int tx, int tq, Pk<OC> own[NJ]) {
+  constexpr int G = ST <= 1 ? 0 : ST - 1;
+  constexpr int TY = 8 * NJ;
+  using Gr = Grp<G, TY>;
+  constexpr int kPx = kT * TY;
+#pragma unroll
+  for (int j = 0; j <= NJ; ++j) {
+    if (j == NJ && !b.h) break;
+    const int ax = j < NJ ? tx : b.hx, ay = j < NJ ? tq + 8 * j : b.hy;
+    Pk<OC> f, r;
+    Fmt::blend(b.q[j], b.L[j], f, r);
+    if (ST == 1) {  // rotation 1 lands on B (+1,0), rotation 3 on C (0,+1)
+      if (in_tile<TY>(ax + 1, ay)) X.put(1 * kPx + ay * kT + ax + 1, f);
+      if (in_tile<TY>(ax, ay + 1)) X.put(2 * kPx + (ay + 1) * kT + ax, r);
+    } else {
+      if (j < NJ) own[j].add(f);
+      const int dx = ax + Gr::ddx, dy = ay + Gr::ddy;
+      if (in_tile<TY>(dx, dy)) X.put((G == 0 ? 0 : G + 2) * kPx + dy * kT + dx, r);
+    }
+  }
+}
+
+template <typename Fmt, int OC, int LD, int NJ, typename XT>
+__device__ __forceinline__ void pipelined_passes(const Tables& t, const uint32_t* __restrict__ tile, const XT& X, int tx,
+                                                 int tq, int tid, Pk<OC> own[NJ]) {
+  StageBuf<Fmt, NJ> A, B;
+  stage_issue<Fmt, LD, 0, NJ>(t, tile, tx, tq, tid, A, nullptr);
+  stage_issue<Fmt, LD, 1, NJ>(t, tile, tx, tq, tid, B, &A);
+  stage_consume<Fmt, OC, 0, NJ>(A, X, tx, tq, own);
+  stage_issue<Fmt, LD, 2, NJ>(t, tile, tx, tq, tid, A, nullptr);
+  stage_consume<Fmt, OC, 1, NJ>(B, X, tx, tq, own);
+  stage_issue<Fmt, LD, 3, NJ>(t, tile, tx, tq, tid, B, nullptr);
+  stage_consume<Fmt, OC, 2, NJ>(A, X, tx, tq, own);
+  stage_issue<Fmt, LD, 4, NJ>(t, tile, tx, tq, tid, A, nullptr);
+  stage_consume<Fmt, OC, 3, NJ>(B, X, tx, tq, own);
+  stage_issue<Fmt, LD, 5, NJ>(t, tile, tx, tq, tid, B, nullptr);
+  stage_consume<Fmt, OC, 4, NJ>(A, X, tx, tq, own);
+  stage_consume<Fmt, OC, 5, NJ>(B, X, tx, tq, own);
+}
+
+template <typename Fmt, int STAGE, int OC, int LD, int MINB, int NJ = 4, bool PIPE = false, bool X6 = false>
 __global__ void __launch_bounds__(256, MINB)
     lut_stage_pw_kernel(Tables t, const uint8_t* __restrict__ in, InAddr ia, int H, int W, int y0, int y1,
                         uint8_t* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int TY = 8 * NJ, kTileRows = TY + 2 * kHalo;
   uint32_t* tile = reinterpret_cast<uint32_t*>(smem_raw);
-  Pk<OC>* X = reinterpret_cast<Pk<OC>*>(smem_raw + kTileRows * kPitch * 4);
+  Xch<OC, X6> X;
+  X.init(smem_raw + kTileRows * kPitch * 4, 7 * kT * TY);
   const int bx = blockIdx.x * kT, by = y0 + blockIdx.y * TY, p = blockIdx.z;
   const uint8_t* src = in + (long long)(p / ia.channels) * ia.batch_stride + (long long)(p % ia.channels) * ia.chan_stride;
   const int tid = threadIdx.x;
@@ -263,11 +369,15 @@ __global__ void __launch_bounds__(256, MINB)
   Pk<OC> own[NJ];
 #pragma unroll
   for (int j = 0; j < NJ; ++j) own[j].zero();
-  group_pass<Fmt, OC, LD, 0, NJ>(t, tile, X, tx, tq, tid, own);
-  group_pass<Fmt, OC, LD, 1, NJ>(t, tile, X, tx, tq, tid, own);
-  group_pass<Fmt, OC, LD, 2, NJ>(t, tile, X, tx, tq, tid, own);
-  group_pass<Fmt, OC, LD, 3, NJ>(t, tile, X, tx, tq, tid, own);
-  group_pass<Fmt, OC, LD, 4, NJ>(t, tile, X, tx, tq, tid, own);
+  if (PIPE) {
+    pipelined_passes<Fmt, OC, LD, NJ>(t, tile, X, tx, tq, tid, own);
+  } else {
+    group_pass<Fmt, OC, LD, 0, NJ>(t, tile, X, tx, tq, tid, own);
+    group_pass<Fmt, OC, LD, 1, NJ>(t, tile, X, tx, tq, tid, own);
+    group_pass<Fmt, OC, LD, 2, NJ>(t, tile, X, tx, tq, tid, own);
+    group_pass<Fmt, OC, LD, 3, NJ>(t, tile, X, tx, tq, tid, own);
+    group_pass<Fmt, OC, LD, 4, NJ>(t, tile, X, tx, tq, tid, own);
+  }
   __syncthreads();
 
   const int x = bx + tx;
@@ -278,7 +388,7 @@ __global__ void __launch_bounds__(256, MINB)
     if (y >= y1) continue;
     Pk<OC> s = own[j];
 #pragma unroll
-    for (int a = 0; a < 7; ++a) s.add(X[a * kT * TY + ty * kT + tx]);
+    for (int a = 0; a < 7; ++a) s.add(X.get(a * kT * TY + ty * kT + tx));
     int n[3];
     s.get(n);
 #pragma unroll
@@ -295,8 +405,8 @@ __global__ void __launch_bounds__(256, MINB)
   }
 }
 
-template <int OC, int NJ = 4>
-constexpr size_t smem_bytes() { return (size_t)(8 * NJ + 2 * kHalo) * kPitch * 4 + (size_t)7 * kT * 8 * NJ * sizeof(Pk<OC>); }
+template <int OC, int NJ = 4, bool X6 = false>
+constexpr size_t smem_bytes() { return (size_t)(8 * NJ + 2 * kHalo) * kPitch * 4 + (size_t)7 * kT * 8 * NJ * Xch<OC, X6>::kBytes; }
 
 }  // namespace pwk
 
@@ -363,6 +473,26 @@ int launch_stage_pw(const lerf_luts_impl* L, int stage, const uint8_t* in, const
   }
   using pwk::FmtPW;
   pwk::Tables t;
+#define LERF_GO_PIPE(B)                                                                                                       \
+  {                                                                                                                            \
+    static bool attr_set = false;                                                                                              \
+    if (!attr_set) {                                                                                                           \
+      LERF_CUDA(cudaFuncSetAttribute(pwk::lut_stage_pw_kernel<FmtPW<3>, 2, 3, 1, B, 4, true>,                                   \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pwk::smem_bytes<3>()));                   \
+      attr_set = true;                                                                                                         \
+    }                                                                                                                          \
+    pwk::lut_stage_pw_kernel<FmtPW<3>, 2, 3, 1, B, 4, true><<<grid, 256, pwk::smem_bytes<3>(), st>>>(t, in, ia, H, W, y0, y1, out); \
+  }
+#define LERF_GO_X6(B)                                                                                                         \
+  {                                                                                                                            \
+    static bool attr_set = false;                                                                                              \
+    if (!attr_set) {                                                                                                           \
+      LERF_CUDA(cudaFuncSetAttribute(pwk::lut_stage_pw_kernel<FmtPW<3>, 2, 3, 1, B, 4, false, true>,                            \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pwk::smem_bytes<3, 4, true>()));          \
+      attr_set = true;                                                                                                         \
+    }                                                                                                                          \
+    pwk::lut_stage_pw_kernel<FmtPW<3>, 2, 3, 1, B, 4, false, true><<<grid, 256, pwk::smem_bytes<3, 4, true>(), st>>>(t, in, ia, H, W, y0, y1, out); \
+  }
 #ifdef LERF_EXPERIMENTS
   // (x) 32 x 8 tiles, one pixel per thread, for launches that do not fill the GPU (one 256 x 256 image is 192 blocks of
   // 32 x 32): four times the blocks, but half again as many halo windows -- measured SLOWER on cfg-1 (21.7 vs 17.8 us).
@@ -399,6 +529,11 @@ int launch_stage_pw(const lerf_luts_impl* L, int stage, const uint8_t* in, const
       case 1: LERF_GO(FmtPW<3>, 2, 3, 0, 3) break;
       case 2: LERF_GO(FmtPW<3>, 2, 3, 1, 2) break;
       case 3: LERF_GO_SMALL(FmtPW<3>, 3) break;
+      case 4: LERF_GO_PIPE(2) break;
+      case 5: LERF_GO_PIPE(3) break;
+      case 6: LERF_GO_PIPE(1) break;
+      case 7: LERF_GO_X6(4) break;
+      case 8: LERF_GO_X6(3) break;
       default: LERF_GO(FmtPW<3>, 2, 3, 1, 3)
     }
   } else {
@@ -415,6 +550,8 @@ int launch_stage_pw(const lerf_luts_impl* L, int stage, const uint8_t* in, const
   else LERF_GO(FmtPW<1>, 2, 1, 1, 3)
 #endif
 #undef LERF_GO
+#undef LERF_GO_PIPE
+#undef LERF_GO_X6
 #ifdef LERF_EXPERIMENTS
 #undef LERF_GO_SMALL
 #endif

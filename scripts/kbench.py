@@ -57,7 +57,7 @@ for kind in os.environ.get("KB_KINDS", "natural,uniform").split(","):
             print("%-8s stage1 cell, carve-out %3d %%     %8.1f us/frame" % (kind, pct, timeit(lambda: lp.lut_stage1(luts, frames, out=feat))), flush=True)
         L.lerf_debug_carveout(-1)
     codes = lp.lut_stage2(luts, ref_feat)
-    s2_variants = ((0, "production (pw minb3)"), (70, "max-tap v10"), (1, "row-major minb4"), (23, "cell-48B minb3")) + tuple((60 + k, "max-tap v%d" % k) for k in range(13)) + ((42, "mix rm+max-tap 8/12"), (80, "pw minb3"), (81, "pw L1 minb3"), (82, "pw minb2"))
+    s2_variants = ((0, "production (pw minb3)"), (70, "max-tap v10"), (1, "row-major minb4"), (23, "cell-48B minb3")) + tuple((60 + k, "max-tap v%d" % k) for k in range(13)) + ((42, "mix rm+max-tap 8/12"), (80, "pw minb3"), (81, "pw L1 minb3"), (82, "pw minb2"), (84, "pw pipelined minb2"), (85, "pw pipelined minb3"), (87, "pw 6-byte exchange minb4"), (88, "pw 6-byte exchange minb3"))
     if ONLY == "pw":
         s2_variants = tuple(x for x in s2_variants if x[0] in (0, 70) or x[0] >= 80)
     for v, name in (s2_variants[:1] if ONLY == "prod" else s2_variants):
