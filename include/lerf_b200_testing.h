@@ -40,7 +40,8 @@ void lerf_debug_force_generic(int on);
 void lerf_debug_warp_records(int on);
 
 /* Integer-scale resampler: 0 = production; 10 = production arithmetic with the byte-store uint8 epilogue of round 1;
- * 11 = geometry factors from kernel parameters instead of immediates (what odd scales use); (x) 1 = hoisted-FP64 form,
+ * 11 = geometry factors from kernel parameters instead of immediates (what odd scales use); 12 = 11 + the interleaved
+ * uint8 tile copied out by lanes (funnel-shifted 128-bit stores) instead of bulk stores; (x) 1 = hoisted-FP64 form,
  * 2 / 5 = plain form at 4 / 5 blocks per SM, 4 = production form at 5 blocks per SM.  All stay within the 1e-4 bar. */
 void lerf_debug_resize_variant(int variant);
 

@@ -52,14 +52,14 @@ __global__ void __launch_bounds__(kCX* kCY, MINB)
 }
 
 // uint8 outputs through a staged tile (resample_int.cuh): CH = 1 planar, CH = 3 interleaved
-template <int S, int CH, bool CG>
+template <int S, int CH, bool CG, bool TMA = true>
 __global__ void __launch_bounds__(kCX* kCY, 4)
     resize_sr_int_gauss_u8_kernel(const uint8_t* __restrict__ feat, const uint8_t* __restrict__ codes, int H, int W, int oH,
                                   int oW, const __grid_constant__ IntGeom<S> g, const CoefTabs* __restrict__ ct, int ly0,
                                   int oy0, int oy1, unsigned char* __restrict__ out) {
   __shared__ Smem sm;
   __shared__ OutTile<S, CH> ot;
-  resize_int_u8_body<S, CH, CG>(feat, codes, H, W, oH, oW, g, ct, ly0, oy0, oy1, out, blockIdx.x, blockIdx.y, blockIdx.z, sm, ot);
+  resize_int_u8_body<S, CH, CG, TMA>(feat, codes, H, W, oH, oW, g, ct, ly0, oy0, oy1, out, blockIdx.x, blockIdx.y, blockIdx.z, sm, ot);
 }
 
 template <int S, bool CG>
@@ -76,9 +76,9 @@ template <int S>
 static int launch_int(const lerf_sr_plan_impl* P, const uint8_t* feat, const uint8_t* codes, int planes, int channels,
                       float max_sigma, int oy0, int oy1, void* out, int fmt, cudaStream_t st) {
 #ifdef LERF_EXPERIMENTS
-  const int rv = g_dbg.resize_variant;
+  const int rv = g_dbg.resize_variant == 12 ? 11 : g_dbg.resize_variant;
 #else
-  const int rv = g_dbg.resize_variant == 11 ? 11 : 0;  // 11: geometry from kernel parameters (the flavour of odd scales)
+  const int rv = g_dbg.resize_variant == 11 || g_dbg.resize_variant == 12 ? 11 : 0;  // 11: geometry from kernel parameters (the flavour of odd scales); 12: 11 + HWC tile copied out by lanes instead of bulk stores
 #endif
   const IntGeom<S> g = make_geom<S>(P, max_sigma, /*unsigned_form=*/rv == 0 || rv == 4 || rv == 11);
   const CoefTabs* ct = plan_coef_tabs(P, max_sigma, st);
@@ -108,7 +108,8 @@ static int launch_int(const lerf_sr_plan_impl* P, const uint8_t* feat, const uin
     if constexpr (sizeof(OutTile<S, 3>) + sizeof(Smem) <= 48 * 1024) {
       if (fmt == LERF_OUT_U8_HWC && channels == 3 && planes % 3 == 0) {
         grid.z = planes / 3;
-        if (cg) resize_sr_int_gauss_u8_kernel<S, 3, true><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, ly0, oy0, oy1, (unsigned char*)out);
+        if (g_dbg.resize_variant == 12) resize_sr_int_gauss_u8_kernel<S, 3, false, false><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, ly0, oy0, oy1, (unsigned char*)out);
+        else if (cg) resize_sr_int_gauss_u8_kernel<S, 3, true><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, ly0, oy0, oy1, (unsigned char*)out);
         else resize_sr_int_gauss_u8_kernel<S, 3, false><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, ly0, oy0, oy1, (unsigned char*)out);
         LERF_LAUNCHED();
         return LERF_OK;

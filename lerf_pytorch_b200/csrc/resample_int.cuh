@@ -419,7 +419,7 @@ __device__ __forceinline__ void copy_tile_out(const OutTile<S, CH>& ot, unsigned
 // uint8 outputs of the integer-scale Gaussian resampler through a staged tile.  CH = 1: planar [P][oH][oW], one plane per
 // block (blockIdx.z = plane).  CH = 3: interleaved [B][oH][oW][3], one image per block (blockIdx.z = batch index), the
 // three colour planes one after the other.
-template <int S, int CH, bool CG>
+template <int S, int CH, bool CG, bool TMA = true>
 __device__ __forceinline__ void resize_int_u8_body(const uint8_t* __restrict__ feat, const uint8_t* __restrict__ codes, int H, int W,
                                                    int oH, int oW, const IntGeom<S>& g, const CoefTabs* __restrict__ ct, int ly0,
                                                    int oy0, int oy1, unsigned char* __restrict__ out, int bxi, int byi, int bz,
@@ -432,6 +432,20 @@ __device__ __forceinline__ void resize_int_u8_body(const uint8_t* __restrict__ f
   const int lx = lx0 + tx, ly = lyb + ty;
   const bool active = lx <= W - 1 && ly <= H - 1;
   const int oyb = S * ly + g.ph_y;
+  // valid part of the tile: rows inside the band and the image, columns inside the image
+  const int oyt = S * lyb + g.ph_y;                       // output row of tile row 0
+  const int ox0 = S * lx0 + g.ph_x;                       // output column of tile byte 0 (pixel units)
+  const int r_lo = max(max(oy0, 0) - oyt, 0), r_hi = min(min(oy1, oH) - oyt, OutTile<S, CH>::kRows);
+  const int jlo = max(0, -ox0) * CH, jhi = min(kCX * S, oW - ox0) * CH;
+  unsigned char* base = out + (long long)bz * oH * oW * CH;  // planar: plane bz; HWC: image bz
+  const long long row_pitch = (long long)oW * CH, col0 = (long long)ox0 * CH;
+  // Bulk-store path (TMA engine, cp.async.bulk): when the output row pitch is a multiple of 16 bytes every row segment of
+  // the tile has the SAME misalignment `mis` against 16 bytes.  The tile is then staged at byte offset `mis` of its shared
+  // rows -- shared and global addresses congruent mod 16 -- so the aligned middle of every row goes out as ONE bulk copy
+  // issued by one thread per row; only the ragged ends (< 16 bytes each) are stored by lanes.  Byte-granular staging only
+  // (CH > 1): the packed-word staging of the planar form needs 4-byte aligned shared addresses.
+  const bool bulk = TMA && CH > 1 && (row_pitch & 15) == 0;
+  const int mis = bulk ? (int)((uintptr_t)(base + (long long)oyt * row_pitch + col0) & 15) : 0;
 #pragma unroll 1
   for (int c = 0; c < CH; ++c) {
     __syncthreads();  // tables staged / the previous plane's coefficient tiles are no longer read
@@ -439,7 +453,7 @@ __device__ __forceinline__ void resize_int_u8_body(const uint8_t* __restrict__ f
     __syncthreads();
     if (active) {
       gauss_cell_rowq<S, CG>(sm, g, tx, ty, oyb, oy0, oy1, [&](int mr, const uint32_t* res) {
-        unsigned char* row = &ot.b[ty * S + mr][OutTile<S, CH>::kSlack];
+        unsigned char* row = &ot.b[ty * S + mr][OutTile<S, CH>::kSlack + mis];
         if (CH == 1 && S == 4) {
           *reinterpret_cast<uint32_t*>(row + 4 * tx) = pack4(res[0], res[1 % S], res[2 % S], res[3 % S]);
         } else {
@@ -449,15 +463,31 @@ __device__ __forceinline__ void resize_int_u8_body(const uint8_t* __restrict__ f
       });
     }
   }
+  if (bulk) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk-copy engine
   __syncthreads();
-  // valid part of the tile: rows inside the band and the image, columns inside the image
-  const int oyt = S * lyb + g.ph_y;                       // output row of tile row 0
-  const int ox0 = S * lx0 + g.ph_x;                       // output column of tile byte 0 (pixel units)
-  const int r_lo = max(max(oy0, 0) - oyt, 0), r_hi = min(min(oy1, oH) - oyt, OutTile<S, CH>::kRows);
-  const int jlo = max(0, -ox0) * CH, jhi = min(kCX * S, oW - ox0) * CH;
-  if (r_lo >= r_hi) return;
-  unsigned char* base = out + (long long)bz * oH * oW * CH;  // planar: plane bz; HWC: image bz
-  copy_tile_out<S, CH>(ot, base, (long long)oW * CH, (long long)ox0 * CH, oyt, r_lo, r_hi, jlo, jhi, tid);
+  if (r_lo >= r_hi || jlo >= jhi) return;
+  if (bulk) {
+    const int ja = min(jlo + ((16 - ((mis + jlo) & 15)) & 15), jhi);  // head = [jlo, ja)
+    const int nb = (jhi - ja) & ~15;                                  // bytes of the aligned middle
+    if (tid < r_hi - r_lo && nb > 0) {
+      const int r = r_lo + tid;
+      unsigned char* gdst = base + (long long)(oyt + r) * row_pitch + col0 + ja;
+      const uint32_t ssrc = (uint32_t)__cvta_generic_to_shared(&ot.b[r][OutTile<S, CH>::kSlack + mis + ja]);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(nb) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    // ragged ends, one lane per byte
+    for (int idx = tid; idx < (r_hi - r_lo) * 32; idx += kCX * kCY) {
+      const int r = r_lo + (idx >> 5), k = idx & 31;
+      unsigned char* grow = base + (long long)(oyt + r) * row_pitch + col0;
+      const int jb = ja + nb;
+      const int j = k < 16 ? jlo + k : jb + (k - 16);
+      if (k < 16 ? j < ja : j < jhi) __stcg(grow + j, ot.b[r][OutTile<S, CH>::kSlack + mis + j]);
+    }
+    if (tid < r_hi - r_lo && nb > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile is read before the block retires
+    return;
+  }
+  copy_tile_out<S, CH>(ot, base, row_pitch, col0, oyt, r_lo, r_hi, jlo, jhi, tid);
 }
 
 // Planar uint8 output for S = 4 and S = 8 without a staged tile.  A x4 cell owns output columns 4*lx + 2 .. 4*lx + 5: its four

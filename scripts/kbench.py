@@ -108,6 +108,12 @@ for kind in os.environ.get("KB_KINDS", "natural,uniform").split(","):
             assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 1e-4, "uint8 epilogues disagree"
             print("%-8s resize %-20s %8.1f us/frame" % (kind, "int-scale " + fmt + " r1 bytes", timeit(lambda: rs.resize_codes(ref_feat, codes, out_format=fmt, out=o2))), flush=True)
             L.lerf_debug_resize_variant(0)
+            if fmt == "u8_hwc":  # tile copied out by lanes (funnel-shifted 128-bit stores) instead of bulk stores
+                L.lerf_debug_resize_variant(12)
+                o3 = rs.resize_codes(ref_feat, codes, out_format=fmt)
+                assert torch.equal(o3, out), "bulk-store copy-out differs"
+                print("%-8s resize %-20s %8.1f us/frame" % (kind, "int-scale u8_hwc lanes", timeit(lambda: rs.resize_codes(ref_feat, codes, out_format=fmt, out=o3))), flush=True)
+                L.lerf_debug_resize_variant(0)
     if ONLY not in ("prod", "pw"):
         out = rs.resize_codes(ref_feat, codes, out_format="f32")
         for v in (0, 1, 2, 4, 5):

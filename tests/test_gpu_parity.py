@@ -371,12 +371,12 @@ def test_resize_kernel_variants_within_tolerance(lp, orc, luts):
     L = lp.lib()
     try:
         want = orc.to_uint8_hwc(ref)
-        for v in (0, 10, 11) + ((1, 2, 4, 5) if L.lerf_build_has_experiments() else ()):
+        for v in (0, 10, 11, 12) + ((1, 2, 4, 5) if L.lerf_build_has_experiments() else ()):
             L.lerf_debug_resize_variant(v)
             out = sr(_cuda(img), out_format="f32").cpu().numpy().astype(np.float64)
             print("resize variant %d: max-abs err %.3g" % (v, _maxabs(out, ref)))
             assert _maxabs(out, ref) <= 1e-4, v  # north_star tolerance for fp32 output
-            for fmt in ("u8", "u8_hwc"):  # shuffle / staged-tile epilogues (0, 11) and the byte-store one (10)
+            for fmt in ("u8", "u8_hwc"):  # shuffle / staged-tile epilogues (0, 11; 12: tile copied out by lanes, not bulk stores) and the byte-store one (10)
                 u8 = sr(_cuda(img), out_format=fmt).cpu().numpy()
                 u8 = np.transpose(u8, (1, 2, 0)) if fmt == "u8" else u8
                 assert np.abs(u8.astype(int) - want.astype(int)).max() <= 1, (v, fmt)
