@@ -172,6 +172,16 @@ int lerf_warp_f32(int kind, const float* img, const float* h0, const float* h1, 
                   int H, int W, int oH, int oW, const double minv[9], int pad0_y, int pad0_x,
                   float max_sigma, float* out, lerf_stream_t stream);
 
+/* lerf_warp / lerf_warp_f32 with the reference's NON-DEFAULT operator parameters: `support` taps per axis (support_sz of
+ * the warp classes, :497 / :580) and the np.pad mode LERF_PAD_* of the image (:559; taps are clipped to in-1 in padded
+ * coordinates, :397-398, so only the LEADING pad is ever read; the hypers replicate).  pad0_y / pad0_x are the leading pads
+ * for THIS support.  Give feat + codes (uint8; any out_format) or img + h0[, h1, h2] (float32; LERF_OUT_F32), the other
+ * group NULL.  No mask (its support is 1 whatever this one is: use lerf_warp with out = NULL).  Float64 operation-order
+ * kernel only. */
+int lerf_warp_ex(int kind, const uint8_t* feat, const uint8_t* codes, const float* img, const float* h0, const float* h1,
+                 const float* h2, int planes, int channels, int H, int W, int oH, int oW, const double minv[9], int support,
+                 int pad_mode, int pad0_y, int pad0_x, float max_sigma, void* out, int out_format, lerf_stream_t stream);
+
 /* Fixed-kernel warps, the baselines the reference compares LeRF with: Warp2dNumpy.warp
  * (resize_right2d_numpy.py:409-449) with a separable kernel LERF_WARP_*.  img: DEVICE planar [P][H][W], float32 or
  * (img_is_u8 != 0) uint8; out: DEVICE float32 planar [P][oH][oW]; pad0_y/pad0_x: leading pads for THIS kernel's support

@@ -38,6 +38,8 @@ PROTOTYPES = {
                          _c_p, _c_i, _c_i, _c_i, _c_p]),
     "lerf_warp_f32": (_c_i, [_c_i, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p, _c_i, _c_i, _c_f,
                              _c_p, _c_p]),
+    "lerf_warp_ex": (_c_i, [_c_i, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p, _c_i, _c_i, _c_i, _c_i,
+                            _c_f, _c_p, _c_i, _c_p]),
     "lerf_warp_fixed_support": (_c_i, [_c_i]),
     "lerf_warp_fixed": (_c_i, [_c_i, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p, _c_i, _c_i, _c_p, _c_p]),
     "lerf_sr_scratch_bytes": (_c_sz, [_c_i, _c_i, _c_i, _c_i]),

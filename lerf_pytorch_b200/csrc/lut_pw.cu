@@ -414,8 +414,9 @@ constexpr size_t smem_bytes() { return (size_t)(8 * NJ + 2 * kHalo) * kPitch * 4
 // copies (family f reads table f >> 1) and the cell-pair tables.
 int build_pw_tables(lerf_luts_impl* L) {
   const int oC = L->oC2;
-  const size_t b1 = pw::table_bytes(1), b2 = pw::table_bytes(oC);
+  const size_t b2 = pw::table_bytes(oC);
 #ifdef LERF_EXPERIMENTS
+  const size_t b1 = pw::table_bytes(1);
   const size_t off2 = 6 * b1;
 #else
   const size_t off2 = 0;

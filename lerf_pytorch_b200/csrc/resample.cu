@@ -272,6 +272,7 @@ struct WarpGeom {
   int H, W, oH, oW;
   int pad0_y, pad0_x;            // support-2 leading pads (:363-369)
   int mpad0_y, mpad0_x, border;  // nearest-neighbour mask geometry (eval_lut_warp.py:197-204)
+  int support, pad_mode;         // lerf_warp_ex: taps per axis and np.pad mode of the image (2 / 'constant' otherwise)
 };
 
 __constant__ double kEps32 = 1.1920928955078125e-07;
@@ -306,6 +307,43 @@ __global__ void __launch_bounds__(256)
   }
   if (!out) return;
 
+  if (g.support != 2 || g.pad_mode != 0) {  // non-default operator parameters (r2): any support, np.pad mode of the image
+    const int supp = g.support;
+    const int lr = (int)ceil(pr0 - 0.5 * (double)supp - kEps32) + g.pad0_y;
+    const int lc = (int)ceil(pc0 - 0.5 * (double)supp - kEps32) + g.pad0_x;
+    const double pr = pr0 + (double)g.pad0_y, pc = pc0 + (double)g.pad0_x;
+    const long long plane_sz = (long long)H * W;
+    for (int p = 0; p < planes; ++p) {
+      double m = -INFINITY, sum = 0.0, acc = 0.0;
+      for (int pass = (KIND == LERF_KIND_GAUSS ? 0 : 1); pass < 3; ++pass)  // Gaussian: max exponent, sum, products; linear: sum, products
+        for (int a = 0; a < supp; ++a)
+          for (int b = 0; b < supp; ++b) {
+            const int fr = clampi2(lr + b, 0, H - 1), fc = clampi2(lc + a, 0, W - 1);  // clipped in padded coordinates (:397-398)
+            const double dr = pr - (double)fr, dc = pc - (double)fc;
+            const int sr = fr - g.pad0_y, sc = fc - g.pad0_x;
+            const long long off = (long long)max(sr, 0) * W + max(sc, 0);  // hypers: 'edge'
+            double w;
+            if (KIND == LERF_KIND_GAUSS) {
+              float rho, s_x, s_y;
+              hyp.gauss(tab, plane_sz, p, off, max_sigma, rho, s_x, s_y);
+              const double e = gauss_exponent(rho, s_x, s_y, dr, dc);
+              if (pass == 0) { m = fmax(m, e); continue; }
+              w = exp(e - m);
+            } else {
+              const double al = (double)hyp.alpha(tab, plane_sz, p, off, max_sigma);
+              w = lin_alpha(dr, al) * lin_alpha(dc, al);
+            }
+            if (pass == 1) { sum += w; continue; }
+            const int iy = pad_src(sr, H, g.pad_mode), ix = pad_src(sc, W, g.pad_mode);
+            const double v = (iy >= 0 && ix >= 0) ? (double)load_img(img + (long long)p * plane_sz + (long long)iy * W + ix) : 0.0;
+            acc += v * (w / sum);
+          }
+      const long long ip = ((long long)p * g.oH + oy) * g.oW + ox;
+      const long long ih = (((long long)(p / channels) * g.oH + oy) * g.oW + ox) * channels + (p % channels);
+      store_sample<FMT>(out, 0, ip, ih, acc);
+    }
+    return;
+  }
   const int lr = (int)ceil(pr0 - 1.0 - kEps32) + g.pad0_y;  // :347-352, :366
   const int lc = (int)ceil(pc0 - 1.0 - kEps32) + g.pad0_x;
   const double pr = pr0 + (double)g.pad0_y, pc = pc0 + (double)g.pad0_x;  // :367
@@ -423,6 +461,7 @@ static int fill_geom(WarpGeom& g, int H, int W, int oH, int oW, const double min
   for (int i = 0; i < 9; ++i) g.m[i] = minv[i];
   g.H = H; g.W = W; g.oH = oH; g.oW = oW;
   g.pad0_y = pad0_y; g.pad0_x = pad0_x; g.mpad0_y = mpy; g.mpad0_x = mpx; g.border = border;
+  g.support = 2; g.pad_mode = 0;
   return LERF_OK;
 }
 
@@ -639,6 +678,35 @@ int lerf_warp_f32(int kind, const float* img, const float* h0, const float* h1, 
   FloatSrc hyp{h0, h1, h2};
   if (kind == LERF_KIND_GAUSS)
     return launch_warp<LERF_KIND_GAUSS>(img, hyp, g, planes, 1, max_sigma, out, LERF_OUT_F32, nullptr, (cudaStream_t)stream);
+  return launch_warp<LERF_KIND_LINEAR>(img, hyp, g, planes, 1, max_sigma, out, LERF_OUT_F32, nullptr, (cudaStream_t)stream);
+}
+
+int lerf_warp_ex(int kind, const uint8_t* feat, const uint8_t* codes, const float* img, const float* h0, const float* h1,
+                 const float* h2, int planes, int channels, int H, int W, int oH, int oW, const double minv[9], int support,
+                 int pad_mode, int pad0_y, int pad0_x, float max_sigma, void* out, int out_format, lerf_stream_t stream) {
+  if (kind != LERF_KIND_GAUSS && kind != LERF_KIND_LINEAR) return fail(LERF_EINVAL, "lerf_warp_ex: unknown kind %d", kind);
+  const bool u8 = feat != nullptr;
+  if (u8 ? !codes : (!img || !h0)) return fail(LERF_EINVAL, "lerf_warp_ex: give feat + codes (uint8) or img + h0[, h1, h2] (float32)");
+  if (kind == LERF_KIND_LINEAR) { h1 = h0; h2 = h0; }
+  if (!u8 && (!h1 || !h2)) return fail(LERF_EINVAL, "lerf_warp_ex: null hyper plane");
+  if (!out) return fail(LERF_EINVAL, "lerf_warp_ex: null output");
+  if (support < 1 || support > 64) return fail(LERF_EINVAL, "lerf_warp_ex: support %d outside [1,64]", support);
+  if (pad_mode < LERF_PAD_CONSTANT || pad_mode > LERF_PAD_WRAP) return fail(LERF_EINVAL, "lerf_warp_ex: unknown pad_mode %d", pad_mode);
+  if (planes < 0 || channels < 1 || (planes % channels)) return fail(LERF_EINVAL, "lerf_warp_ex: bad planes/channels");
+  if (!u8 && out_format != LERF_OUT_F32) return fail(LERF_EINVAL, "lerf_warp_ex: float32 inputs give float32 output");
+  WarpGeom g;
+  int rc = fill_geom(g, H, W, oH, oW, minv, pad0_y, pad0_x, 0, 0, 0);
+  if (rc) return rc;
+  if (oH == 0 || oW == 0 || planes == 0) return LERF_OK;
+  g.support = support;
+  g.pad_mode = pad_mode;
+  if (u8) {
+    CodeSrc hyp{codes};
+    if (kind == LERF_KIND_GAUSS) return launch_warp<LERF_KIND_GAUSS>(feat, hyp, g, planes, channels, max_sigma, out, out_format, nullptr, (cudaStream_t)stream);
+    return launch_warp<LERF_KIND_LINEAR>(feat, hyp, g, planes, channels, max_sigma, out, out_format, nullptr, (cudaStream_t)stream);
+  }
+  FloatSrc hyp{h0, h1, h2};
+  if (kind == LERF_KIND_GAUSS) return launch_warp<LERF_KIND_GAUSS>(img, hyp, g, planes, 1, max_sigma, out, LERF_OUT_F32, nullptr, (cudaStream_t)stream);
   return launch_warp<LERF_KIND_LINEAR>(img, hyp, g, planes, 1, max_sigma, out, LERF_OUT_F32, nullptr, (cudaStream_t)stream);
 }
 

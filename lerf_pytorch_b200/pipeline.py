@@ -203,14 +203,14 @@ class GraphedSR(object):
 class LerfWarp(object):
     """Homographic warping through the LUT path (one image per call, like the reference)."""
 
-    def __init__(self, luts, max_sigma=10, support_sz=2, border=4):
+    def __init__(self, luts, max_sigma=10, support_sz=2, border=4, pad_mode="constant"):
         assert isinstance(luts, LutSet)
         self.luts = luts
         self.border = border  # eval_lut_warp.py:36
         if luts.linear:
             self.warper = AmplifiedLinearWarp2d()  # eval_lut_warp.py:38
         else:
-            self.warper = SteeringGaussianWarp2d(support_sz=support_sz, max_sigma=max_sigma)
+            self.warper = SteeringGaussianWarp2d(support_sz=support_sz, max_sigma=max_sigma, pad_mode=pad_mode)
 
     def batch(self, imgs, matrices, out_hw, out_format="f32", with_mask=True, out=None, masks=None):
         """Several (image, homography) pairs of one input size onto one canvas size: ``imgs`` uint8 CUDA [B,H,W,C],

@@ -246,8 +246,10 @@ class Warp2d(object):
     kind = None
 
     def __init__(self, support_sz=4, device="GPU", pad_mode="constant"):
-        if pad_mode != "constant":
-            raise NotImplementedError("only pad_mode='constant' is implemented")
+        if pad_mode not in _PAD_MODES:
+            raise NotImplementedError("pad_mode=%r: one of %s" % (pad_mode, sorted(_PAD_MODES)))
+        if not 1 <= int(support_sz) <= 64:
+            raise ValueError("support_sz must be in 1..64")
         self.eps = _EPS
         self.device = device
         self.support_sz = support_sz
@@ -273,9 +275,12 @@ class Warp2d(object):
         self.minv = np.ascontiguousarray(np.linalg.inv(m), dtype=np.float64)  # :327
         self.pad0 = _warp_pad0(self.minv, self.in_sz, self.support_sz)
 
+    def _default_params(self):
+        """True for the parameters eval_lut_warp.py runs with (--suppSize 2, constant padding): the tuned kernels; anything
+        else goes through lerf_warp_ex (operation-order float64, any support, np.pad modes)."""
+        return self.support_sz == 2 and self.pad_mode == "constant"
+
     def _check(self, H, W):
-        if self.support_sz != 2:
-            raise NotImplementedError("support_sz=%r: only the default --suppSize 2 is implemented" % (self.support_sz,))
         if [H, W] != self.in_sz:
             raise ValueError("input is %dx%d but set_shape() was given %dx%d" % (H, W, self.in_sz[0], self.in_sz[1]))
 
@@ -296,12 +301,23 @@ class Warp2d(object):
         if with_mask and mask is None:
             mask = torch.empty((oH, oW), dtype=torch.uint8, device=dev)
         mp = _warp_pad0(self.minv, self.in_sz, 1) if with_mask else (0, 0)
+        L = _lib.lib()
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().lerf_warp(self.kind, feat.contiguous().data_ptr(), codes.contiguous().data_ptr(), P,
-                                            channels, H, W, oH, oW, self.minv.ctypes.data, self.pad0[0], self.pad0[1],
-                                            float(self.max_sigma), out.data_ptr(), _FMT[out_format],
-                                            mask.data_ptr() if with_mask else None, mp[0], mp[1], mask_border,
-                                            _stream_ptr(dev)))
+            if self._default_params():
+                _lib.check(L.lerf_warp(self.kind, feat.contiguous().data_ptr(), codes.contiguous().data_ptr(), P,
+                                       channels, H, W, oH, oW, self.minv.ctypes.data, self.pad0[0], self.pad0[1],
+                                       float(self.max_sigma), out.data_ptr(), _FMT[out_format],
+                                       mask.data_ptr() if with_mask else None, mp[0], mp[1], mask_border,
+                                       _stream_ptr(dev)))
+            else:
+                _lib.check(L.lerf_warp_ex(self.kind, feat.contiguous().data_ptr(), codes.contiguous().data_ptr(), None,
+                                          None, None, None, P, channels, H, W, oH, oW, self.minv.ctypes.data,
+                                          int(self.support_sz), _PAD_MODES[self.pad_mode], self.pad0[0], self.pad0[1],
+                                          float(self.max_sigma), out.data_ptr(), _FMT[out_format], _stream_ptr(dev)))
+                if with_mask:   # the mask is a support-1 nearest warp whatever this operator's support is
+                    _lib.check(L.lerf_warp(LERF_KIND_GAUSS, None, None, 0, 1, H, W, oH, oW, self.minv.ctypes.data, 0, 0,
+                                           1.0, None, LERF_OUT_F32, mask.data_ptr(), mp[0], mp[1], mask_border,
+                                           _stream_ptr(dev)))
         return (out, mask) if with_mask else out
 
     def _warp_f32(self, input, h0, h1, h2):
@@ -314,9 +330,16 @@ class Warp2d(object):
         out = torch.empty((P, oH, oW), dtype=torch.float32, device=dev)
         p = [h.data_ptr() if h is not None else None for h in hs]
         with torch.cuda.device(dev):
-            _lib.check(_lib.lib().lerf_warp_f32(self.kind, img.data_ptr(), p[0], p[1], p[2], P, H, W, oH, oW,
-                                                self.minv.ctypes.data, self.pad0[0], self.pad0[1],
-                                                float(self.max_sigma), out.data_ptr(), _stream_ptr(dev)))
+            if self._default_params():
+                _lib.check(_lib.lib().lerf_warp_f32(self.kind, img.data_ptr(), p[0], p[1], p[2], P, H, W, oH, oW,
+                                                    self.minv.ctypes.data, self.pad0[0], self.pad0[1],
+                                                    float(self.max_sigma), out.data_ptr(), _stream_ptr(dev)))
+            else:
+                _lib.check(_lib.lib().lerf_warp_ex(self.kind, None, None, img.data_ptr(), p[0], p[1], p[2], P, 1, H, W,
+                                                   oH, oW, self.minv.ctypes.data, int(self.support_sz),
+                                                   _PAD_MODES[self.pad_mode], self.pad0[0], self.pad0[1],
+                                                   float(self.max_sigma), out.data_ptr(), LERF_OUT_F32,
+                                                   _stream_ptr(dev)))
         out = out.reshape(lead + (oH, oW))
         return out.cpu().numpy() if was_numpy else out
 

@@ -433,15 +433,20 @@ static void warp_pads(const double* minv, int H, int W, int oH, int oW, int supp
 /* SteeringGaussianWarp2dNumpy.warp (:516-577) for kind 0, AmplifiedLinearWarp2dNumpy.warp
  * (:597-635) for kind 1, on the geometry of Warp2dNumpy.get_distance (:371-407):
  * taps clipped to [0, in-1] in PADDED coordinates after the pad shift (:396-398),
- * distances against the clipped taps (:400-403).  0/0 gives NaN as in numpy. */
-int lerf_oracle_warp(int kind, const float* img, const float* h0, const float* h1,
-                     const float* h2, int C, int H, int W, const double* minv, int oH,
-                     int oW, float max_sigma, double* out) {
-  const int supp = 2;
+ * distances against the clipped taps (:400-403).  0/0 gives NaN as in numpy.
+ * Any support size; pad_mode = the np.pad mode of the image (only the LEADING pad can be
+ * reached: taps are clipped to in-1), the hypers replicate. */
+int lerf_oracle_warp_ex(int kind, const float* img, const float* h0, const float* h1,
+                        const float* h2, int C, int H, int W, const double* minv, int oH,
+                        int oW, float max_sigma, int supp, int pad_mode, double* out) {
+  if (supp < 1 || supp > 64) return 2;
   int p0x, p0y;
   warp_pads(minv, H, W, oH, oW, supp, &p0x, &p0y);
+  const int n = supp * supp;
 #pragma omp parallel for schedule(static)
   for (int ox = 0; ox < oH; ++ox) {
+    double* wts = (double*)malloc(sizeof(double) * 2 * n);
+    double* nb = wts + n;
     for (int oy = 0; oy < oW; ++oy) {
       double px, py;
       warp_project(minv, ox, oy, H, W, &px, &py);
@@ -449,9 +454,8 @@ int lerf_oracle_warp(int kind, const float* img, const float* h0, const float* h
       px += (double)p0x; py += (double)p0y;                                      /* :367 */
       for (int c = 0; c < C; ++c) {
         const size_t pl = (size_t)c * H * W;
-        double wts[4], nb[4];
-        for (int a = 0; a < 2; ++a)
-          for (int b = 0; b < 2; ++b) {
+        for (int a = 0; a < supp; ++a)
+          for (int b = 0; b < supp; ++b) {
             const int fx = clampi(lx + b, 0, H - 1), fy = clampi(ly + a, 0, W - 1); /* :397-398 */
             const double dx = px - (double)fx, dy = py - (double)fy;
             const int sx_ = fx - p0x, sy_ = fy - p0y;
@@ -462,19 +466,26 @@ int lerf_oracle_warp(int kind, const float* img, const float* h0, const float* h
               wgt = sk_weight(dec_rho(h0[hi]), h1[hi] * max_sigma, h2[hi] * max_sigma, dx, dy);
             else
               wgt = linear_weight(max_sigma * dec_rho(h0[hi]), dx, dy);
-            wts[a * 2 + b] = wgt;
-            const int inside = (sx_ >= 0 && sy_ >= 0); /* upper side cannot leave: fx <= in-1 */
-            nb[a * 2 + b] = inside ? (double)img[pl + (size_t)sx_ * W + sy_] : 0.0;
+            wts[a * supp + b] = wgt;
+            const int ix = pad_src(fx, p0x, H, pad_mode), iy = pad_src(fy, p0y, W, pad_mode);
+            nb[a * supp + b] = (ix >= 0 && iy >= 0) ? (double)img[pl + (size_t)ix * W + iy] : 0.0;
           }
         double s = 0.0;
-        for (int k = 0; k < 4; ++k) s += wts[k];
+        for (int k = 0; k < n; ++k) s += wts[k];
         double acc = 0.0;
-        for (int k = 0; k < 4; ++k) acc += nb[k] * (wts[k] / s);
+        for (int k = 0; k < n; ++k) acc += nb[k] * (wts[k] / s);
         out[((size_t)c * oH + ox) * oW + oy] = acc;
       }
     }
+    free(wts);
   }
   return 0;
+}
+
+int lerf_oracle_warp(int kind, const float* img, const float* h0, const float* h1,
+                     const float* h2, int C, int H, int W, const double* minv, int oH,
+                     int oW, float max_sigma, double* out) {
+  return lerf_oracle_warp_ex(kind, img, h0, h1, h2, C, H, W, minv, oH, oW, max_sigma, 2, 0, out);
 }
 
 /* NearestWarp2dNumpy (:460-467): support 1, box2d weight (interp_methods.py:67-70,

@@ -868,6 +868,50 @@ def test_non_default_operator_parameters_vs_reference_goldens(lp, orc):
         assert _maxabs(lin.resize(img, hy[0]), G["linear_%d" % i]) <= FP32_TOL, case
 
 
+def _warp_close(got, ref, tol, jumps=0):
+    """Equal NaN patterns and values within tol, except at most ``jumps`` pixels (the |d| = 1 cut of the linear kernel,
+    resize_right2d_numpy.py:590-600: a tap at distance 1 to the last ulp falls on either side of it)."""
+    bad = np.isnan(got) != np.isnan(ref)
+    m = ~np.isnan(got) & ~np.isnan(ref)
+    bad |= m & (np.abs(np.where(m, got, 0) - np.where(m, ref, 0)) > tol)
+    assert int(bad.any(axis=0).sum()) <= jumps, int(bad.any(axis=0).sum())
+
+
+def test_warp_non_default_operator_parameters_vs_reference_goldens(lp, orc):
+    """support_sz 1 / 3 / 4 / 6 and np.pad modes for the WARP classes through lerf_warp_ex: the float32-hyper API against
+    goldens generated by the reference (tests/golden/make_golden_general.py)."""
+    G = golden("resize_general")
+    img, hy = G["img"], [G["h0"], G["h1"], G["h2"]]
+    oshape = [3] + [int(v) for v in G["warp_out_hw"]]
+    for i, case in enumerate(G["warp_cases"]):
+        supp, pm, mi = str(case).split("|")
+        g = lp.SteeringGaussianWarp2dNumpy(support_sz=int(supp), max_sigma=10, pad_mode=pm)
+        g.set_shape(list(img.shape), G["warp_M"][int(mi)], oshape)
+        _warp_close(g.warp(img, *hy), G["warp_gauss_%d" % i], FP32_TOL)
+        lin = lp.AmplifiedLinearWarp2dNumpy(support_sz=int(supp), pad_mode=pm)
+        lin.set_shape(list(img.shape), G["warp_M"][int(mi)], oshape)
+        _warp_close(lin.warp(img, hy[0]), G["warp_linear_%d" % i], FP32_TOL, jumps=3)
+
+
+@pytest.mark.parametrize("supp,pad", [(4, "constant"), (3, "edge"), (2, "reflect")])
+def test_whole_warp_path_with_non_default_parameters_vs_oracle(lp, orc, luts, supp, pad):
+    """--suppSize 4 / other paddings through the whole LeRF-G warp path (uint8 codes -> lerf_warp_ex, every output format,
+    the support-1 mask beside it) against the oracle."""
+    ld, ls = luts["g"]
+    img = natural_image(46, 41, 52)
+    M = np.array([[1.21, 0.11, -3.0], [-0.08, 1.17, 2.5], [3e-4, -2e-4, 1.0]])
+    oshape = (57, 50)
+    w = lp.LerfWarp(ls, support_sz=supp, pad_mode=pad)
+    out, mask = w(_cuda(img), M, oshape, out_format="f32")
+    ref, rmask, _, _ = orc.lerf_warp(img, ld, M, (3,) + oshape, linear=False, supp=supp, pad_mode=pad)
+    assert np.array_equal(mask.cpu().numpy(), rmask)
+    _warp_close(out.cpu().numpy(), ref, FP32_TOL)
+    u8, _ = w(_cuda(img), M, oshape, out_format="u8_hwc")
+    want = orc.to_uint8_hwc(np.nan_to_num(ref))
+    valid = np.isfinite(ref).all(axis=0)
+    assert np.abs(u8.cpu().numpy().astype(int) - want.astype(int))[valid].max() <= 1
+
+
 @pytest.mark.parametrize("supp,scale", [(4, 4), (4, 2.5), (3, 2)])
 def test_whole_path_with_support_4_vs_oracle(lp, orc, luts, supp, scale):
     """--suppSize 4 through the whole LeRF-G path (uint8 codes, row bands, uint8 epilogue) against the oracle."""

@@ -178,3 +178,30 @@ def test_resize_non_default_parameters_match_reference_float64():
         assert np.array_equal(np.isnan(got), np.isnan(ref)), case
         m = np.isfinite(ref)
         assert np.max(np.abs(got[m] - ref[m])) <= 1e-9, case
+
+
+def _warp_close(got, ref, tol, jumps=0):
+    """Equal NaN patterns and values within tol, except at most ``jumps`` pixels: the linear kernel 1 - |d|/alpha... is cut
+    at |d| = 1 (resize_right2d_numpy.py:590-600), and a tap whose projected distance is 1 to the last ulp falls on either
+    side of the cut depending on the BLAS that multiplied the homography."""
+    assert got.shape == ref.shape
+    bad = np.isnan(got) != np.isnan(ref)
+    m = ~np.isnan(got) & ~np.isnan(ref)
+    bad |= m & (np.abs(np.where(m, got, 0) - np.where(m, ref, 0)) > tol)
+    assert int(bad.any(axis=0).sum()) <= jumps, int(bad.any(axis=0).sum())
+
+
+def test_warp_non_default_parameters_match_reference_float64():
+    """support_sz 1 / 3 / 4 / 6 and np.pad modes for the WARP classes (resize_right2d_numpy.py:363-369, :397-398, :559):
+    the oracle against goldens generated by the reference (tests/golden/make_golden_general.py)."""
+    G = golden("resize_general")
+    img, hy = G["img"], [G["h0"], G["h1"], G["h2"]]
+    oshape = [3] + [int(v) for v in G["warp_out_hw"]]
+    for i, case in enumerate(G["warp_cases"]):
+        supp, pm, mi = str(case).split("|")
+        g = orc.SteeringGaussianWarp2dNumpy(support_sz=int(supp), max_sigma=10, pad_mode=pm)
+        g.set_shape(list(img.shape), G["warp_M"][int(mi)], oshape)
+        _warp_close(g.warp(img, *hy), G["warp_gauss_%d" % i], 1e-9)
+        lin = orc.AmplifiedLinearWarp2dNumpy(support_sz=int(supp), pad_mode=pm)
+        lin.set_shape(list(img.shape), G["warp_M"][int(mi)], oshape)
+        _warp_close(lin.warp(img, hy[0]), G["warp_linear_%d" % i], 1e-9, jumps=3)
