@@ -30,9 +30,10 @@ void lerf_debug_lut_variant(int stage, int variant);
  * (0,0,0 = plain layout; default 9,5,3).  Results never depend on it. */
 void lerf_debug_cell_hash(int ha, int hb, int hc);
 
-/* 0 = production dispatch (cell-owner kernel for integer scales, tile kernel for other scales >= 1, fast warp kernel);
- * 1 = only the float64 operation-order kernels (the parity path); 2 = like 0 without the cell-owner kernel, so integer
- * scales take the tile kernel too.  All must agree within the fp32 tolerance. */
+/* 0 = production dispatch (cell-owner kernel for integer scales, any-scale cell kernel for other scales from x3 per axis
+ * up, tile kernel for the remaining scales >= 1, fast warp kernel); 1 = only the float64 operation-order kernels (the
+ * parity path); 2 = like 0 without the cell-owner kernels, so every scale takes the tile kernel; 3 = the any-scale cell
+ * kernel wherever it applies (scales in [1, 4]), integer scales included.  All must agree within the fp32 tolerance. */
 void lerf_debug_force_generic(int on);
 
 /* lerf_warp's fast Gaussian kernel: 1 (default) = every input sample is first decoded into a 32-byte record and a tap

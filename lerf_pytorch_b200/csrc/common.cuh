@@ -24,7 +24,7 @@ struct DebugState {
   int cell_hash[3] = {9, 5, 3};   // swizzle baked into the NEXT LutSet's cell tables
   int resize_variant = 0;         // integer-scale resampler flavour
   int u8_staged = 1;              // 0 = byte-store uint8 epilogue of r1
-  int force_generic = 0;          // 1 = float64 parity kernels only; 2 = no cell-owner kernel
+  int force_generic = 0;          // 1 = float64 parity kernels only; 2 = no cell-owner kernel; 3 = the any-scale cell kernel wherever it applies
   int warp_records = 1;           // 0 = table form of the fast warp kernel
   int pipe_enabled = 0, pipe_minb = 3, pipe_group = 0;  // (x) role-interleaved pipeline kernel
   int l2_window = 0;              // lerf_luts_pin_l2: 0 = cell-packed block, 1 = paired-window block
@@ -109,6 +109,9 @@ struct lerf_sr_plan_impl {
   double aa_scale;
   int tile_ok;     // every 32 x 32 output group has its taps in a 33 x 33 input window (any scale >= 1), |dist| <= 1: resample_tile.cu
   int tile_rows;   // output rows per block of the tile kernel: the largest of 128, 96, 64, 32 whose taps fit 33 input rows
+  int* cell_y;     // device [H + 2]: cell_y[l + 1] = first output row whose first tap is >= l (l = -1 .. H), so the outputs of
+  int* cell_x;     // device [W + 2]  cell l are [cell[l + 1], cell[l + 2]); built when tile_ok (resample_tile.cu cell kernel)
+  int cell_max_y, cell_max_x;  // longest run
   static constexpr int kCoefSlots = 8;
   void* coef_dev[kCoefSlots];    // rsi::CoefTabs per max_sigma (resample_int.cu plan_coef_tabs), immutable once uploaded
   float coef_sigma[kCoefSlots];
@@ -146,6 +149,8 @@ int resize_sr_int_linear(const lerf_sr_plan_impl* P, const uint8_t* feat, const 
 // resample_tile.cu: fast paths for uint8 code inputs; return -1 when they do not apply
 int resize_sr_tile(int kind, const lerf_sr_plan_impl* P, const uint8_t* feat, const uint8_t* codes, int planes, int channels,
                    float max_sigma, int oy0, int oy1, void* out, int fmt, cudaStream_t st);
+int resize_sr_cell(int kind, const lerf_sr_plan_impl* P, const uint8_t* feat, const uint8_t* codes, int planes, int channels,
+                   float max_sigma, int oy0, int oy1, void* out, int fmt, bool any_scale, cudaStream_t st);
 int warp_fast(int kind, const uint8_t* feat, const uint8_t* codes, int planes, int channels, int H, int W, int oH, int oW,
               const double minv[9], int pad0_y, int pad0_x, int mpad0_y, int mpad0_x, int border, float max_sigma, void* out,
               int fmt, uint8_t* mask, cudaStream_t st);

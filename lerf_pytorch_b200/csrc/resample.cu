@@ -16,6 +16,9 @@
 // weights' low bits -- and accumulates/divides in float64.  Nothing but the output touches HBM.
 #include <math.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 
 namespace lerf {
@@ -522,6 +525,25 @@ int lerf_sr_plan_create(int H, int W, int oH, int oW, const int32_t* left_y, con
   for (int o = 0; o < oW && P->tile_ok; ++o)
     if (left_x[o + 31 < oW ? o + 31 : oW - 1] - left_x[o] > 31 || fabs(dist_x[2 * o]) > 1.0000005 || fabs(dist_x[2 * o + 1]) > 1.0000005)
       P->tile_ok = 0;
+  if (P->tile_ok) {  // cell runs for the cell kernel (resample_tile.cu): the outputs whose first tap is l are contiguous
+    auto runs = [&](const int32_t* left, int in, int on, int** dev, int& longest) {
+      std::vector<int> cs(in + 2);
+      int o = 0;
+      for (int l = -1; l <= in; ++l) {
+        while (o < on && left[o] < l) ++o;
+        cs[l + 1] = o;
+      }
+      longest = 0;
+      for (int l = 0; l <= in; ++l) longest = std::max(longest, cs[l + 1] - cs[l]);
+      up((void**)dev, cs.data(), sizeof(int) * (in + 2));
+    };
+    runs(left_y, H, oH, &P->cell_y, P->cell_max_y);
+    runs(left_x, W, oW, &P->cell_x, P->cell_max_x);
+    if (e != cudaSuccess) {
+      lerf_sr_plan_destroy(reinterpret_cast<lerf_sr_plan_t*>(P));
+      return fail(LERF_ECUDA, "lerf_sr_plan_create: upload failed: %s", cudaGetErrorString(e));
+    }
+  }
   *out = reinterpret_cast<lerf_sr_plan_t*>(P);
   return LERF_OK;
 }
@@ -569,6 +591,7 @@ void lerf_sr_plan_destroy(lerf_sr_plan_t* plan) {
   lerf_sr_plan_impl* P = reinterpret_cast<lerf_sr_plan_impl*>(plan);
   cudaSetDevice(P->device);
   cudaFree(P->left_y); cudaFree(P->dist_y); cudaFree(P->left_x); cudaFree(P->dist_x);
+  cudaFree(P->cell_y); cudaFree(P->cell_x);
   for (int i = 0; i < P->coef_n; ++i) cudaFree(P->coef_dev[i]);
   free(P->h_left_y);
   delete P;
@@ -597,13 +620,18 @@ int lerf_resize_sr(int kind, const lerf_sr_plan_t* plan, const uint8_t* feat, co
     return launch_sr<LERF_KIND_LINEAR>(P, feat, hyp, planes, channels, max_sigma, oy0, oy1, out, out_format, (cudaStream_t)stream);
   }
   if (kind == LERF_KIND_GAUSS) {
-    if (P->int_scale && g_dbg.force_generic == 0) {  // periodic geometry: cell-owner kernel (resample_int.cu)
+    if (P->int_scale && g_dbg.force_generic == 0) {  // periodic geometry: integer-scale cell-owner kernel (resample_int.cu)
       rc = resize_sr_int_gauss(P, feat, codes, planes, channels, max_sigma, oy0, oy1, out, out_format, (cudaStream_t)stream);
       if (rc != -1) return rc;
     }
   }
   if (kind == LERF_KIND_LINEAR && P->int_scale && g_dbg.force_generic == 0) {  // periodic geometry, LeRF-L (resample_int.cu)
     rc = resize_sr_int_linear(P, feat, codes, planes, channels, max_sigma, oy0, oy1, out, out_format, (cudaStream_t)stream);
+    if (rc != -1) return rc;
+  }
+  if (g_dbg.force_generic == 0 || g_dbg.force_generic == 3) {  // scales in [3, 4] per axis: any-scale cell kernel (resample_tile.cu)
+    rc = resize_sr_cell(kind, P, feat, codes, planes, channels, max_sigma, oy0, oy1, out, out_format, g_dbg.force_generic == 3,
+                        (cudaStream_t)stream);
     if (rc != -1) return rc;
   }
   if (g_dbg.force_generic != 1) {  // any scale >= 1: tile kernel (resample_tile.cu); the float64 kernels below are the parity path

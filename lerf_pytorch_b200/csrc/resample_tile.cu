@@ -200,6 +200,172 @@ __global__ void __launch_bounds__(kOX* kTY)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// SR cell kernel (r2): the cell-owner layout of resample_int.cuh for ANY scale in [1, NMAX] per axis (non-integer,
+// anisotropic, non-periodic).  For a scale >= 1 the outputs whose first tap is input sample l form a contiguous run
+// [start[l], start[l + 1]) on each axis (plan->cell_y / cell_x, built from the caller's tables); one thread owns one cell
+// = one (row run) x (column run), reads its 2 x 2 taps ONCE, keeps the column runs' distances in registers (at most
+// NMAX columns) and walks its rows.  What this saves over the tile kernel above: the ~300-instruction per-thread set-up
+// per 4..16 samples, the tap re-read test per row, and half the float64 work of an exponent -- the ROWQ form of
+// resample_int.cuh, `rowq[t] = fma(a'_t, -dr^2, magic)` and `b'_t * -dr` once per output row, then
+// `fma(b'dr_t, dc, fma(c'_t, -dc^2, rowq[t]))` per exponent.  The amplified-linear kind evaluates exactly the tile
+// kernel's expression (bit-identical results).  A block = 32 x 8 cells, its taps a 33 x 9 window in shared memory.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kGX = 32, kGY = 8;
+constexpr int kCellMaxY = 8;  // longest row run the kernel takes (its block stages kGY * kCellMaxY row distances)
+
+struct SmemCG {
+  CoefTabs tab;
+  double sA[kGY + 1][kGX + 1], sB[kGY + 1][kGX + 1], sC[kGY + 1][kGX + 1];
+  float sV[kGY + 1][kGX + 1];
+};
+struct SmemCL {
+  double al[256];
+  double sA[kGY + 1][kGX + 1];
+  float sV[kGY + 1][kGX + 1];
+};
+
+template <int KIND, int FMT, int NMAX, bool CLAMP>
+__global__ void __launch_bounds__(kGX* kGY, 3)
+    resize_sr_cell_kernel(const uint8_t* __restrict__ feat, const uint8_t* __restrict__ codes, int H, int W, int oH, int oW,
+                          const int* __restrict__ cell_y, const double* __restrict__ dist_y, const int* __restrict__ cell_x,
+                          const double* __restrict__ dist_x, const CoefTabs* __restrict__ ct, const FixQ fq, float max_sigma,
+                          int channels, int ly0, int oy0, int oy1, void* __restrict__ out) {
+  __shared__ typename std::conditional<KIND == LERF_KIND_GAUSS, SmemCG, SmemCL>::type sm;
+  __shared__ double2 s_dy[kGY * kCellMaxY];  // the block's output rows: distances to tap 0 / tap 1
+  __shared__ double2 s_dx[kGX * NMAX];       // the block's output columns
+  __shared__ int s_cx[kGX + 1];              // column runs of the block's cells
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  const int p = blockIdx.z;
+  const int lxb = (int)blockIdx.x * kGX - 1, lyb = ly0 + (int)blockIdx.y * kGY;  // first cell of the block (cells start at -1)
+  const long long plane_sz = (long long)H * W;
+  const uint8_t* fp = feat + (long long)p * plane_sz;
+  if constexpr (KIND == LERF_KIND_GAUSS) {
+    sm.tab.s2[tid] = __ldg(ct->s2 + tid);
+    sm.tab.sg[tid] = __ldg(ct->sg + tid);
+    sm.tab.rl[tid] = __ldg(ct->rl + tid);
+  } else {  // alpha = fl(max_sigma * rho) in float32 like numpy (:249-250), promoted exactly
+    const float h = __fdiv_rn((float)tid, 255.0f);
+    sm.al[tid] = (double)__fmul_rn(max_sigma, __fsub_rn(__fmul_rn(h, 2.0f), 1.0f));
+  }
+  const int yb0 = __ldg(cell_y + lyb + 1);                              // first output row of the block's cells
+  const int yb1 = __ldg(cell_y + min(lyb + kGY, H) + 1);                // one past their last
+  const int xb0 = __ldg(cell_x + lxb + 1);
+  const int xb1 = __ldg(cell_x + min(lxb + kGX, W) + 1);
+  if (tid < yb1 - yb0) s_dy[tid] = __ldg(reinterpret_cast<const double2*>(dist_y) + yb0 + tid);  // <= kGY * kCellMaxY (host check)
+  if (tid < xb1 - xb0) s_dx[tid] = __ldg(reinterpret_cast<const double2*>(dist_x) + xb0 + tid);  // <= kGX * NMAX
+  if (tid <= kGX) s_cx[tid] = __ldg(cell_x + min(lxb + tid, W) + 1);
+  __syncthreads();
+  const uint8_t* cp = codes + (long long)p * (KIND == LERF_KIND_GAUSS ? 3 : 1) * plane_sz;
+  for (int i = tid; i < (kGY + 1) * (kGX + 1); i += kGX * kGY) {
+    const int r = i / (kGX + 1), c = i - r * (kGX + 1);
+    const int sy = lyb + r, sx = lxb + c;
+    const int cy = min(max(sy, 0), H - 1), cx = min(max(sx, 0), W - 1);  // hypers: 'edge' (:172-174, :252-254)
+    const long long off = (long long)cy * W + cx;
+    if constexpr (KIND == LERF_KIND_GAUSS) {
+      const int kr = __ldcg(cp + off), kx = __ldcg(cp + plane_sz + off), ky = __ldcg(cp + 2 * plane_sz + off);
+      sm.sA[r][c] = sm.tab.s2[kx];
+      sm.sC[r][c] = sm.tab.s2[ky];
+      sm.sB[r][c] = sm.tab.rl[kr] * sm.tab.sg[kx] * sm.tab.sg[ky];
+    } else {
+      sm.sA[r][c] = sm.al[__ldcg(cp + off)];
+    }
+    sm.sV[r][c] = (sy == cy && sx == cx) ? (float)__ldcg(fp + off) : 0.0f;  // image: 'constant' 0 (:208, :268)
+  }
+  __syncthreads();
+  const int lx = lxb + tx, ly = lyb + ty;
+  if (lx > W - 1 || ly > H - 1) return;
+  const int xs = s_cx[tx], nx = s_cx[tx + 1] - xs;  // the cell's column run (nx <= NMAX: host check)
+  const int ys = max(__ldg(cell_y + ly + 1), oy0), ye = min(__ldg(cell_y + ly + 2), oy1);
+  if (nx <= 0 || ys >= ye) return;
+  double ca[4], cb[4], cc[4];  // Gaussian: a', b', -c' per tap;  linear: ca = alpha
+  float dv[4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {  // patch order a*2+b as in the reference (:95-98)
+      const int t = a * 2 + b;
+      ca[t] = sm.sA[ty + b][tx + a];
+      if constexpr (KIND == LERF_KIND_GAUSS) {
+        cb[t] = sm.sB[ty + b][tx + a];
+        cc[t] = -sm.sC[ty + b][tx + a];
+      }
+      dv[t] = sm.sV[ty + b][tx + a];
+    }
+  const float v0 = dv[0];
+  dv[1] -= v0; dv[2] -= v0; dv[3] -= v0;  // exact: integers in [-255, 255]
+  double dc[NMAX][2];     // Gaussian: dc;  linear: |dc|
+  float vc[NMAX][2];      // linear only: [|dc| <= 1]
+#pragma unroll
+  for (int mc = 0; mc < NMAX; ++mc) {
+    const double2 d = s_dx[min(xs - xb0 + mc, kGX * NMAX - 1)];  // columns past the run: any finite value (never stored)
+    if constexpr (KIND == LERF_KIND_GAUSS) {
+      dc[mc][0] = d.x; dc[mc][1] = d.y;
+    } else {
+      dc[mc][0] = fabs(d.x); dc[mc][1] = fabs(d.y);
+      vc[mc][0] = dc[mc][0] <= 1.0 ? 1.0f : 0.0f;
+      vc[mc][1] = dc[mc][1] <= 1.0 ? 1.0f : 0.0f;
+    }
+  }
+  const long long ip = ((long long)p * oH + ys) * oW + xs;                                             // planar index
+  const long long ih = (((long long)(p / channels) * oH + ys) * oW + xs) * channels + (p % channels);  // interleaved index
+  // one pointer per thread, advanced row by row; column mc is a constant offset from it
+  constexpr int kEl = FMT == LERF_OUT_F32 ? 4 : 1;
+  unsigned char* op = (unsigned char*)out + (FMT == LERF_OUT_U8_HWC ? ih : ip) * kEl;
+  const long long row_step = (long long)oW * kEl * (FMT == LERF_OUT_U8_HWC ? channels : 1);
+  const int col_step = FMT == LERF_OUT_U8_HWC ? channels : 1;
+  const double2* dyp = s_dy + (ys - yb0);
+#pragma unroll 1
+  for (int oy = ys; oy < ye; ++oy, op += row_step, ++dyp) {
+    const double2 dr = *dyp;  // one address per warp: a shared-memory broadcast
+    float res[NMAX];
+    if constexpr (KIND == LERF_KIND_GAUSS) {
+      const double drb[2] = {dr.x, dr.y};
+      double rowq[4], bdr[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        rowq[t] = fma(ca[t], -drb[t & 1] * drb[t & 1], fq.magic);  // >= magic: the quadratic form's row term is >= 0
+        bdr[t] = cb[t] * -drb[t & 1];
+      }
+#pragma unroll
+      for (int mc = 0; mc < NMAX; ++mc) {
+        unsigned q[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)  // dc (b' -dr + -c' dc) + rowq: Horner in dc, ONE rounding at the fixed-point scale here
+          q[t] = (unsigned)__double2loint(fma(dc[mc][t >> 1], fma(cc[t], dc[mc][t >> 1], bdr[t]), rowq[t]));
+        res[mc] = combine_uq(q, dv, v0, fq.neg_scale);
+      }
+    } else {
+      const double adr[2] = {fabs(dr.x), fabs(dr.y)};
+      const float vr[2] = {adr[0] <= 1.0 ? 1.0f : 0.0f, adr[1] <= 1.0 ? 1.0f : 0.0f};
+      double lr[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) lr[t] = fma(-ca[t], adr[t & 1], 1.0);
+#pragma unroll
+      for (int mc = 0; mc < NMAX; ++mc) {
+        float w[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {  // lin_weight<CLAMP> with the row factor hoisted
+          const double lc = fma(-ca[t], dc[mc][t >> 1], 1.0);
+          const float valid = vr[t & 1] * vc[mc][t >> 1];
+          w[t] = CLAMP ? fmaxf((float)lr[t], 0.0f) * fmaxf((float)lc, 0.0f) * valid : (float)(lr[t] * lc) * valid;
+        }
+        res[mc] = combine_lin(w, dv, v0);
+      }
+    }
+#pragma unroll
+    for (int mc = 0; mc < NMAX; ++mc)
+      if (mc < nx) {
+        if (FMT == LERF_OUT_F32) {
+          __stcg(reinterpret_cast<float*>(op) + mc, res[mc]);
+        } else {
+          const int qv = min(max(__float2int_rn(res[mc]), 0), 255);  // round half to even, like store1
+          __stcg(op + mc * col_step, (unsigned char)qv);
+        }
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // warp: one thread = one output pixel, all planes; float64 geometry in the reference's operation order
 // ---------------------------------------------------------------------------------------------------------------
 // One 32-byte record per input sample for the Gaussian warp: the tap's three exponent coefficients and its value, so
@@ -441,6 +607,47 @@ int resize_sr_tile(int kind, const lerf_sr_plan_impl* P, const uint8_t* feat, co
   return LERF_OK;
 }
 
+
+// Called by lerf_resize_sr before the tile kernel.  It applies to any scale whose column runs hold at most 4 outputs and
+// whose row runs at most 8, and it PAYS from x3 per axis up (measured, 8 frames 2040x1356, G samples/s cell / tile: x3.5
+// Gaussian 325 / 265, linear 381 / 305; x2.5 207 / 218 and 248 / 282; x1.5 95 / 141 -- a cell of 2 x 2 outputs does not
+// amortise its set-up), so smaller scales stay on the tile kernel unless `any_scale` (lerf_debug_force_generic(3), the
+// parity tests).  Returns -1 when this path does not apply.
+int resize_sr_cell(int kind, const lerf_sr_plan_impl* P, const uint8_t* feat, const uint8_t* codes, int planes, int channels,
+                   float max_sigma, int oy0, int oy1, void* out, int fmt, bool any_scale, cudaStream_t st) {
+  if (!any_scale && (P->oW < 3 * (long long)P->W || P->oH < 3 * (long long)P->H)) return -1;
+  if (!P->tile_ok || !P->cell_x || P->cell_max_x > 4 || P->cell_max_y > kCellMaxY || !(max_sigma >= 0.0f) || max_sigma > 64.0f) return -1;
+  const FixQ fq = make_fixq(max_sigma);
+  const CoefTabs* ct = nullptr;
+  if (kind == LERF_KIND_GAUSS) {
+    ct = plan_coef_tabs(P, max_sigma, st);
+    if (!ct) return fail(LERF_ECUDA, "uploading the hyper decode tables failed");
+  }
+  const int ly0 = P->h_left_y[oy0], ly1 = P->h_left_y[oy1 - 1];
+  dim3 block(kGX * kGY), grid((P->W + 1 + kGX - 1) / kGX, (ly1 - ly0 + 1 + kGY - 1) / kGY, planes);
+#define LERF_GK(K, F, N, CL)                                                                                              \
+  resize_sr_cell_kernel<K, F, N, CL><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, P->cell_y, P->dist_y, \
+                                                             P->cell_x, P->dist_x, ct, fq, max_sigma, channels, ly0, oy0, oy1, out)
+#define LERF_GN(K, F, CL)                         \
+  if (P->cell_max_x <= 2) LERF_GK(K, F, 2, CL);      \
+  else if (P->cell_max_x == 3) LERF_GK(K, F, 3, CL); \
+  else LERF_GK(K, F, 4, CL)
+#define LERF_GO(F)                                                  \
+  if (kind == LERF_KIND_GAUSS) { LERF_GN(LERF_KIND_GAUSS, F, false); }   \
+  else if (max_sigma > 1.0f) { LERF_GN(LERF_KIND_LINEAR, F, true); }    \
+  else { LERF_GN(LERF_KIND_LINEAR, F, false); }
+  switch (fmt) {
+    case LERF_OUT_F32: LERF_GO(LERF_OUT_F32); break;
+    case LERF_OUT_U8: LERF_GO(LERF_OUT_U8); break;
+    case LERF_OUT_U8_HWC: LERF_GO(LERF_OUT_U8_HWC); break;
+    default: return fail(LERF_EINVAL, "unknown out_format %d", fmt);
+  }
+#undef LERF_GO
+#undef LERF_GN
+#undef LERF_GK
+  LERF_LAUNCHED();
+  return LERF_OK;
+}
 
 // Stream-ordered scratch for the records: a library-owned memory pool per device that keeps its memory between calls
 // (the default pool hands it back to the driver at every synchronisation: 6 ms per 100 MB call, measured).

@@ -129,14 +129,15 @@ def tile():
     luts = lp.LutSet(lp.load_lut_dict(os.path.join(LUTS, "lerf-g")), device=dev)
     imgs = natural(8, 1356, 2040, 3000)
     feat, codes = lp.LerfSR(luts, 4).stages(imgs)
-    for sc, force in ((4, 0), (4, 2), (3.5, 0), (2.5, 0), (1.5, 0)):
+    for sc, force in ((4, 0), (4, 3), (4, 2), (3.5, 3), (3.5, 2), (3.2, 3), (3.2, 2), (2.5, 3), (2.5, 2), (1.5, 3), (1.5, 2), ((1.5, 2.0), 3), ((1.5, 2.0), 2)):
         rs = lp.SteeringGaussianResize2d(support_sz=2, max_sigma=10)
-        rs.set_shape([3, 1356, 2040], scale_factors=[sc, sc])
+        rs.set_shape([3, 1356, 2040], scale_factors=list(sc) if isinstance(sc, tuple) else [sc, sc])
         lp.lib().lerf_debug_force_generic(force)
         out = rs.resize_codes(feat, codes)
         ms = timeit(lambda: rs.resize_codes(feat, codes, out=out), 10)
         lp.lib().lerf_debug_force_generic(0)
-        print(json.dumps({"config": "resampler only, LeRF-G x%s, %s kernel" % (sc, "cell-owner" if (sc == 4 and force == 0) else "tile"),
+        name = "tile" if force == 2 else ("cell-owner (integer scale)" if force == 0 else "cell (any scale)")
+        print(json.dumps({"config": "resampler only, LeRF-G x%s, %s kernel" % (sc, name),
                           "ms": round(ms, 4), "G_samples_per_s": round(out.numel() / ms / 1e6, 1)}), flush=True)
 
 
@@ -145,14 +146,15 @@ def lin():
     luts = lp.LutSet(lp.load_lut_dict(os.path.join(LUTS, "lerf-l"), linear=True), linear=True, device=dev)
     imgs = natural(8, 1356, 2040, 3000)
     feat, codes = lp.LerfSR(luts, 4).stages(imgs)
-    for sc, force in ((4, 0), (4, 2), (3, 0), (3, 2)):
+    for sc, force in ((4, 0), (4, 3), (4, 2), (3, 0), (3, 3), (3, 2), (3.5, 3), (3.5, 2), (2.5, 3), (2.5, 2)):
         rs = lp.AmplifiedLinearResize2d()
         rs.set_shape([3, 1356, 2040], scale_factors=[sc, sc])
         lp.lib().lerf_debug_force_generic(force)
         out = rs.resize_codes(feat, codes)
         ms = timeit(lambda: rs.resize_codes(feat, codes, out=out), 10)
         lp.lib().lerf_debug_force_generic(0)
-        print(json.dumps({"config": "resampler only, LeRF-L x%d, %s kernel" % (sc, "cell-owner" if force == 0 else "tile"),
+        name = "tile" if force == 2 else ("cell-owner (integer scale)" if force == 0 else "cell (any scale)")
+        print(json.dumps({"config": "resampler only, LeRF-L x%s, %s kernel" % (sc, name),
                           "ms": round(ms, 4), "G_samples_per_s": round(out.numel() / ms / 1e6, 1)}), flush=True)
 
 

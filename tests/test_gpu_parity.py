@@ -629,6 +629,45 @@ def test_tile_kernel_vs_float64_kernel_and_oracle(lp, orc, luts, model, sh, sw):
         assert np.array_equal(np.transpose(outs[level]["u8"], (1, 2, 0)), outs[level]["u8_hwc"])
 
 
+@pytest.mark.parametrize("model,sh,sw", [("g", 3.5, 3.5), ("g", 1.3, 2.6), ("g", 1.5, 2.0), ("g", 2.5, 2.5), ("g", 1.0, 1.0), ("g", 3.99, 1.01), ("g", 4, 4), ("g", 3.3, 3.7),
+                                         ("l", 3.5, 3.5), ("l", 1.0, 2.25), ("l", 1.5, 1.5), ("l", 2.7, 3.3), ("l", 3, 3)])
+def test_cell_kernel_vs_tile_kernel_and_oracle(lp, orc, luts, model, sh, sw):
+    """The any-scale cell kernel (resample_tile.cu) serves scales from x3 per axis up that the integer-scale kernels do not
+    cover; force_generic 3 routes every scale in [1, 4] through it.  The tile kernel (level 2) is the second implementation:
+    the amplified-linear kind must agree bit for bit, the Gaussian kind within the tolerance (ROWQ rounding order), both
+    with the oracle; row bands reproduce the full run; odd sizes leave ragged last cells."""
+    ld, ls = luts[model]
+    img = uniform_image(78, 67, 93)
+    sr = lp.LerfSR(ls, sh, sw)
+    dimg = _cuda(img)
+    ref, _, _ = orc.lerf_sr(img, ld, sh, sw, linear=(model == "l"))
+    outs = {}
+    try:
+        for level in (3, 2):
+            lp.lib().lerf_debug_force_generic(level)
+            outs[level] = {f: sr(dimg, out_format=f).cpu().numpy() for f in ("f32", "u8", "u8_hwc")}
+            if level == 3:
+                full = torch.from_numpy(outs[3]["f32"]).cuda()
+                band = torch.zeros_like(full)
+                oH = full.shape[-2]
+                for r0, r1 in ((0, 1), (1, oH // 3), (oH // 3, 2 * oH // 3 + 1), (2 * oH // 3 + 1, oH)):
+                    sr(dimg, out_format="f32", rows=(r0, r1), out=band.unsqueeze(0))
+                assert torch.equal(band, full)
+    finally:
+        lp.lib().lerf_debug_force_generic(0)
+    if model == "l":
+        assert np.array_equal(outs[3]["f32"], outs[2]["f32"], equal_nan=True)
+    if sh >= 3 and sw >= 3 and (sh != int(sh) or sw != int(sw)):  # the production dispatch takes the cell kernel here
+        assert np.array_equal(sr(dimg, out_format="f32").cpu().numpy(), outs[3]["f32"], equal_nan=True)
+    for level in (3, 2):
+        err = _maxabs(outs[level]["f32"], ref)
+        print("%s x%sx%s %s kernel: max-abs err %.3g" % (model, sh, sw, "cell" if level == 3 else "tile", err))
+        assert err <= FP32_TOL
+        want = orc.to_uint8_hwc(ref)
+        assert np.max(np.abs(outs[level]["u8_hwc"].astype(int) - want.astype(int))) <= 1
+        assert np.array_equal(np.transpose(outs[level]["u8"], (1, 2, 0)), outs[level]["u8_hwc"])
+
+
 def test_fast_warp_kernel_vs_float64_kernel(lp, orc, luts):
     """lerf_warp takes the fast kernel (resample_tile.cu); force_generic 1 is the float64 operation-order kernel.  Both must
     match the oracle inside the validity mask and give the same mask."""
