@@ -22,7 +22,7 @@ int lerf_build_has_experiments(void);
 
 /* Kernel behind lerf_lut_stage1 (stage = 1) / lerf_lut_stage2 (stage = 2).  0 = production (stage 1: cell-packed tables;
  * stage 2: paired-window tables for oC = 3, cell-packed for oC = 1).  20..39 = cell-packed-table kernel (20 + n: (x) tuning
- * variant n), 80.. = paired-window kernel (stage 2; stage 1 and the cell-pair format 90.. are (x)), 1..19 = (x) row-major
+ * variant n; 27 = one sort per lookup instead of production's two lookups per 16x2 sorting network, in every build), 80.. = paired-window kernel (stage 2; stage 1 and the cell-pair format 90.. are (x)), 1..19 = (x) row-major
  * table kernel, 40..59 = (x) table-format mix, 60..79 = (x) max-tap block kernel (production of round 1).
  * All variants produce identical bytes. */
 void lerf_debug_lut_variant(int stage, int variant);

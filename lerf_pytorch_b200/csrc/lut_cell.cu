@@ -16,12 +16,13 @@ using namespace cellk;
 
 namespace {
 
-template <int STAGE, int OC, int MINB>
+// PAIRED (oC = 1): two lookups per 16x2 sorting network (cell::simplex_pair_of) -- production; false = one sort per lookup.
+template <int STAGE, int OC, int MINB, bool PAIRED = false>
 __global__ void __launch_bounds__(kTX* kTY, MINB)
     lut_stage_cell_kernel(CellTables tabs, const uint8_t* __restrict__ in, InAddr ia, int H, int W, int y0, int y1,
                           uint8_t* __restrict__ out) {
   __shared__ uint32_t tile[kTileWords];
-  lut_stage_cell_body<STAGE, OC>(tabs, in, ia, H, W, y0, y1, out, blockIdx.x, blockIdx.y, blockIdx.z, tile);
+  lut_stage_cell_body<STAGE, OC, PAIRED>(tabs, in, ia, H, W, y0, y1, out, blockIdx.x, blockIdx.y, blockIdx.z, tile);
 }
 
 #ifdef LERF_EXPERIMENTS
@@ -153,10 +154,17 @@ int launch_stage_cell(const lerf_luts_impl* L, int stage, const uint8_t* in, con
   t.h = cell::Hash{(uint32_t)L->cell_hash[0], (uint32_t)L->cell_hash[1], (uint32_t)L->cell_hash[2]};
   dim3 block(kTX * kTY), grid((W + kTX - 1) / kTX, (y1 - y0 + kTY - 1) / kTY, planes);
   if (g_dbg.carveout >= 0) {  // A/B hook; production leaves the driver's choice (the smallest carve-out that fits the blocks)
-    cudaFuncSetAttribute(lut_stage_cell_kernel<1, 1, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, g_dbg.carveout);
-    cudaFuncSetAttribute(lut_stage_cell_kernel<2, 1, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, g_dbg.carveout);
+    cudaFuncSetAttribute(lut_stage_cell_kernel<1, 1, 5, true>, cudaFuncAttributePreferredSharedMemoryCarveout, g_dbg.carveout);
+    cudaFuncSetAttribute(lut_stage_cell_kernel<2, 1, 4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, g_dbg.carveout);
   }
 #define LERF_GO(S, O, B) lut_stage_cell_kernel<S, O, B><<<grid, block, 0, st>>>(t, in, ia, H, W, y0, y1, out)
+#define LERF_GP(S, B) lut_stage_cell_kernel<S, 1, B, true><<<grid, block, 0, st>>>(t, in, ia, H, W, y0, y1, out)
+  if (variant == 7 && (stage == 1 || L->oC2 == 1)) {  // one sort per lookup (the r1 form): second implementation for the tests
+    if (stage == 1) LERF_GO(1, 1, 6);
+    else LERF_GO(2, 1, 4);
+    LERF_LAUNCHED();
+    return LERF_OK;
+  }
 #ifdef LERF_EXPERIMENTS
   if (stage == 1) {
     switch (variant) {
@@ -164,7 +172,9 @@ int launch_stage_cell(const lerf_luts_impl* L, int stage, const uint8_t* in, con
       case 3: LERF_GO(1, 1, 3); break;
       case 5: LERF_GO(1, 1, 5); break;
       case 4: LERF_GO(1, 1, 4); break;
-      default: LERF_GO(1, 1, 6);
+      case 8: LERF_GP(1, 6); break;
+      case 9: LERF_GP(1, 4); break;
+      default: LERF_GP(1, 5);
     }
   } else if (L->oC2 == 3) {
     switch (variant) {
@@ -174,14 +184,14 @@ int launch_stage_cell(const lerf_luts_impl* L, int stage, const uint8_t* in, con
       default: LERF_GO(2, 3, 4);
     }
   } else {
-    LERF_GO(2, 1, 4);
+    LERF_GP(2, 4);
   }
 #else
-  (void)variant;
-  if (stage == 1) LERF_GO(1, 1, 6);
+  if (stage == 1) LERF_GP(1, 5);
   else if (L->oC2 == 3) LERF_GO(2, 3, 4);
-  else LERF_GO(2, 1, 4);
+  else LERF_GP(2, 4);
 #endif
+#undef LERF_GP
 #undef LERF_GO
   LERF_LAUNCHED();
   return LERF_OK;

@@ -56,6 +56,17 @@ LERF_HD int dp4a_ss(uint32_t a, uint32_t b, int c) {  // signed bytes x signed b
 #endif
 }
 
+// (a & ~mask) | (c & mask) as ONE LOP3 (ptxas splits the two-immediate source form into two).
+LERF_HD uint32_t bitsel(uint32_t a, uint32_t c, uint32_t mask) {
+#if defined(__CUDA_ARCH__)
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xB8;" : "=r"(d) : "r"(a), "r"(mask), "r"(c));
+  return d;
+#else
+  return (a & ~mask) | (c & mask);
+#endif
+}
+
 LERF_HD int imax(int a, int b) { return a > b ? a : b; }
 LERF_HD int imin(int a, int b) { return a < b ? a : b; }
 
@@ -90,7 +101,7 @@ LERF_HD Simplex simplex_of(uint32_t xa, uint32_t xb, uint32_t xc, uint32_t xd, c
   const uint32_t acc = ((xa * 16u + xb) * 16u + xc) * 16u + xd;
   // bits 8..11 of acc + ha*xa + hb*xb + hc*xc = (d + ha*a + hb*b + hc*c) mod 16: the X words are zero below bit 8
   const uint32_t mix = xa * h.ha + (xb * h.hb + (xc * h.hc + acc));
-  s.cell = prmt((acc & ~0xF00u) | (mix & 0xF00u), 0u, 0x4421u);
+  s.cell = prmt(bitsel(acc, mix, 0xF00u), 0u, 0x4421u);
   // key = lsb<<24 | msb<<8 | (tap's corner bit & 7) replicated in nibbles 0 and 1.  Sorting descending orders the
   // taps by lsb (ties: any order, the tied vertices get weight 0).
   int k1 = (int)(xa | 0x00u), k2 = (int)(xb | 0x44u), k3 = (int)(xc | 0x22u), k4 = (int)(xd | 0x11u);
@@ -102,7 +113,7 @@ LERF_HD Simplex simplex_of(uint32_t xa, uint32_t xb, uint32_t xc, uint32_t xd, c
   t = imax(k2, k3); k3 = imin(k2, k3); k2 = t;
   const uint32_t u2 = (uint32_t)(k1 | k2), u3 = u2 | (uint32_t)k3;
   // X: nibble 0 = corner of vertex 1, nibble 1 = corner of vertex 3 (nibble 2 is junk, nibble 3 is 0)
-  s.selX = ((uint32_t)k1 & 0xFu) | (u3 & ~0xFu);
+  s.selX = bitsel(u3, (uint32_t)k1, 0xFu);
   // Y: nibble 0 = corner of vertex 2, nibble 1 forced to 7 (vertex 4), nibble 3 = 0 (vertex 0)
   s.selY = u2 | 0x70u;
   const uint32_t a1 = prmt((uint32_t)k1, (uint32_t)k3, 0x2273u);  // [f1, f3, 0, 0]
@@ -111,6 +122,79 @@ LERF_HD Simplex simplex_of(uint32_t xa, uint32_t xb, uint32_t xc, uint32_t xd, c
   s.wX = a1 - a2;                // [f1-f2, f3-f4, 0, 0]          no borrows: the f are sorted
   s.wY = a2 + 0x10000000u - a3;  // [f2-f3, f4,    0, 16-f1]
   return s;
+}
+
+// Unsigned max / min of the two 16-bit halves (VIMNMX.U16x2 on sm_90+).
+LERF_HD uint32_t vmax2(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  uint32_t d;
+  asm("max.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+#else
+  const uint32_t al = a & 0xFFFFu, bl = b & 0xFFFFu, ah = a >> 16, bh = b >> 16;
+  return (al > bl ? al : bl) | ((ah > bh ? ah : bh) << 16);
+#endif
+}
+LERF_HD uint32_t vmin2(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  uint32_t d;
+  asm("min.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+#else
+  const uint32_t al = a & 0xFFFFu, bl = b & 0xFFFFu, ah = a >> 16, bh = b >> 16;
+  return (al < bl ? al : bl) | ((ah < bh ? ah : bh) << 16);
+#endif
+}
+
+// Cell index of one lookup (first half of simplex_of).
+LERF_HD uint32_t cell_of(uint32_t xa, uint32_t xb, uint32_t xc, uint32_t xd, const Hash& h) {
+  const uint32_t acc = ((xa * 16u + xb) * 16u + xc) * 16u + xd;
+  const uint32_t mix = xa * h.ha + (xb * h.hb + (xc * h.hc + acc));
+  return prmt(bitsel(acc, mix, 0xF00u), 0u, 0x4421u);
+}
+
+// TWO lookups through ONE sorting network (r2).  The stage-1 kernel is bound by the ALU pipe and the ten
+// min / max of a lookup's sort are its largest item.  The sort only needs the lsb (4 bits) and the tap's selector bits (one
+// byte), so the keys of two lookups fit the two halves of a register -- half = lsb << 8 | selector bits -- and the 16x2
+// min / max sorts both at once: per pair 4 PRMT to pack + 10 min / max instead of 20.  The selectors come out in the low
+// byte of each sorted half exactly as in simplex_of (a PRMT reads only the low 16 bits of its selector operand; the
+// second lookup's are shifted down); nibble 2 of a selector now holds an lsb, which is junk of weight 0 like before,
+// and nibble 3 stays 0.  The weight bytes are picked from byte 1 (first lookup) / byte 3 (second) of the sorted halves; the zero
+// bytes come from PRMT's sign replication of an lsb byte (<= 15).
+LERF_HD void simplex_pair_of(const uint32_t x1[4], const uint32_t x2[4], const Hash& h, Simplex& s1, Simplex& s2) {
+  s1.cell = cell_of(x1[0], x1[1], x1[2], x1[3], h);
+  s2.cell = cell_of(x2[0], x2[1], x2[2], x2[3], h);
+  // half = [selector bits, lsb]: bytes (x.b2 = 0, x.b3 = lsb) of each lookup's split_px word
+  uint32_t k1 = prmt(x1[0], x2[0], 0x7632u);
+  uint32_t k2 = prmt(x1[1], x2[1], 0x7632u) | 0x00440044u;
+  uint32_t k3 = prmt(x1[2], x2[2], 0x7632u) | 0x00220022u;
+  uint32_t k4 = prmt(x1[3], x2[3], 0x7632u) | 0x00110011u;
+  uint32_t t;
+  t = vmax2(k1, k2); k2 = vmin2(k1, k2); k1 = t;
+  t = vmax2(k3, k4); k4 = vmin2(k3, k4); k3 = t;
+  t = vmax2(k1, k3); k3 = vmin2(k1, k3); k1 = t;
+  t = vmax2(k2, k4); k4 = vmin2(k2, k4); k2 = t;
+  t = vmax2(k2, k3); k3 = vmin2(k2, k3); k2 = t;
+  const uint32_t u2 = k1 | k2, u3 = u2 | k3;
+  const uint32_t selX = bitsel(u3, k1, 0x000F000Fu), selY = u2 | 0x00700070u;
+  s1.selX = selX;
+  s1.selY = selY;
+  s2.selX = selX >> 16;
+  s2.selY = selY >> 16;
+  {
+    const uint32_t a1 = prmt(k1, k3, 0x9951u);  // [f1, f3, 0, 0]
+    const uint32_t a2 = prmt(k2, k4, 0x9951u);  // [f2, f4, 0, 0]
+    const uint32_t a3 = prmt(k3, k1, 0x5991u);  // [f3, 0, 0, f1]
+    s1.wX = a1 - a2;
+    s1.wY = a2 + 0x10000000u - a3;
+  }
+  {
+    const uint32_t a1 = prmt(k1, k3, 0xBB73u);
+    const uint32_t a2 = prmt(k2, k4, 0xBB73u);
+    const uint32_t a3 = prmt(k3, k1, 0x7BB3u);
+    s2.wX = a1 - a2;
+    s2.wY = a2 + 0x10000000u - a3;
+  }
 }
 
 // q = the cell's 16 bytes (x,y = X; z,w = Y).  Returns N = sum_k w_k * vertex_k, |N| <= 2048.

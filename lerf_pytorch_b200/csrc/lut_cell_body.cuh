@@ -36,6 +36,16 @@ __device__ __forceinline__ Simplex simplex_at(const uint32_t* c, const cell::Has
                           c[Tap<MODE, R, 3>::dy * kPitch + Tap<MODE, R, 3>::dx], h);
 }
 
+// Lookups (MODE, RA) and (MODE, RB) through one sorting network (cell::simplex_pair_of).
+template <int MODE, int RA, int RB>
+__device__ __forceinline__ void simplex_pair_at(const uint32_t* c, const cell::Hash& h, Simplex& sa, Simplex& sb) {
+  const uint32_t xa[4] = {c[Tap<MODE, RA, 0>::dy * kPitch + Tap<MODE, RA, 0>::dx], c[Tap<MODE, RA, 1>::dy * kPitch + Tap<MODE, RA, 1>::dx],
+                          c[Tap<MODE, RA, 2>::dy * kPitch + Tap<MODE, RA, 2>::dx], c[Tap<MODE, RA, 3>::dy * kPitch + Tap<MODE, RA, 3>::dx]};
+  const uint32_t xb[4] = {c[Tap<MODE, RB, 0>::dy * kPitch + Tap<MODE, RB, 0>::dx], c[Tap<MODE, RB, 1>::dy * kPitch + Tap<MODE, RB, 1>::dx],
+                          c[Tap<MODE, RB, 2>::dy * kPitch + Tap<MODE, RB, 2>::dx], c[Tap<MODE, RB, 3>::dy * kPitch + Tap<MODE, RB, 3>::dx]};
+  cell::simplex_pair_of(xa, xb, h, sa, sb);
+}
+
 __device__ __forceinline__ int lookup1(const uint8_t* __restrict__ tab, const Simplex& s) {
   const uint4 q = __ldg(reinterpret_cast<const uint4*>(tab) + s.cell);
   return cell::blend(q.x, q.y, q.z, q.w, s);
@@ -67,7 +77,7 @@ struct CellTables {
 constexpr int kTileWords = (kTY + 2 * kHalo) * kPitch;
 
 // `tile` = kTileWords words of shared memory; (bxi, byi, p) = the block's tile column, tile row and plane.
-template <int STAGE, int OC>
+template <int STAGE, int OC, bool PAIRED = false>
 __device__ __forceinline__ void lut_stage_cell_body(const CellTables& tabs, const uint8_t* __restrict__ in, const InAddr& ia,
                                                     int H, int W, int y0, int y1, uint8_t* __restrict__ out, int bxi,
                                                     int byi, int p, uint32_t* tile) {
@@ -90,11 +100,23 @@ __device__ __forceinline__ void lut_stage_cell_body(const CellTables& tabs, cons
 
   if (OC == 1) {
     int n = 0;
+    if (PAIRED) {  // two lookups per sorting network (production)
+#define LERF_P1(M, RA, RB)                                                \
+  {                                                                       \
+    Simplex sa, sb;                                                       \
+    simplex_pair_at<M, RA, RB>(c, tabs.h, sa, sb);                        \
+    n += lookup1(tabs.t[STAGE == 1 ? M : 2 * M + (RA & 1)], sa);          \
+    n += lookup1(tabs.t[STAGE == 1 ? M : 2 * M + (RB & 1)], sb);          \
+  }
+      LERF_P1(0, 0, 1) LERF_P1(0, 2, 3) LERF_P1(1, 0, 1) LERF_P1(1, 2, 3) LERF_P1(2, 0, 1) LERF_P1(2, 2, 3)
+#undef LERF_P1
+    } else {
 #define LERF_L1(M, R) n += lookup1(tabs.t[STAGE == 1 ? M : 2 * M + (R & 1)], simplex_at<M, R>(c, tabs.h));
-    LERF_L1(0, 0) LERF_L1(0, 1) LERF_L1(0, 2) LERF_L1(0, 3)
-    LERF_L1(1, 0) LERF_L1(1, 1) LERF_L1(1, 2) LERF_L1(1, 3)
-    LERF_L1(2, 0) LERF_L1(2, 1) LERF_L1(2, 2) LERF_L1(2, 3)
+      LERF_L1(0, 0) LERF_L1(0, 1) LERF_L1(0, 2) LERF_L1(0, 3)
+      LERF_L1(1, 0) LERF_L1(1, 1) LERF_L1(1, 2) LERF_L1(1, 3)
+      LERF_L1(2, 0) LERF_L1(2, 1) LERF_L1(2, 2) LERF_L1(2, 3)
 #undef LERF_L1
+    }
     int v;
     if (STAGE == 1) {
       v = n <= 0 ? 0 : min(rhe_div(n, 48), 255);

@@ -40,10 +40,14 @@ def timeit(fn):
 for kind in os.environ.get("KB_KINDS", "natural,uniform").split(","):
     frames = (bench.natural_frames_gpu if kind == "natural" else bench.uniform_frames_gpu)(B, 3000, dev)
     ref_feat = None
-    s1_variants = ((0, "cell (production)"), (1, "row-major minb3"), (25, "cell minb5"), (26, "cell minb6"), (80, "pw minb3"), (81, "pw L1 minb3"), (82, "pw minb4"), (83, "pw L1 minb4"), (90, "cell-pair minb4"), (91, "cell-pair minb3"), (92, "cell-pair minb5"), (93, "cell-pair noalloc"))
+    s1_variants = ((0, "cell (production)"), (27, "cell, one sort/lookup"), (28, "cell paired minb6"), (29, "cell paired minb4"), (1, "row-major minb3"), (25, "cell minb5"), (26, "cell minb6"), (80, "pw minb3"), (81, "pw L1 minb3"), (82, "pw minb4"), (83, "pw L1 minb4"), (90, "cell-pair minb4"), (91, "cell-pair minb3"), (92, "cell-pair minb5"), (93, "cell-pair noalloc"))
     if ONLY == "pw":
         s1_variants = tuple(x for x in s1_variants if x[0] == 0 or x[0] >= 80)
+    if ONLY == "s1":
+        s1_variants = s1_variants[:4]
     for v, name in (s1_variants[:1] if ONLY == "prod" else s1_variants):
+        if ONLY == "s1" and v == 0:
+            pass
         L.lerf_debug_lut_variant(1, v)
         feat = lp.lut_stage1(luts, frames)
         if ref_feat is None:
@@ -51,6 +55,8 @@ for kind in os.environ.get("KB_KINDS", "natural,uniform").split(","):
         assert v in (11, 12) or torch.equal(feat, ref_feat), "stage-1 variants disagree"
         print("%-8s stage1 %-24s %8.1f us/frame" % (kind, name, timeit(lambda: lp.lut_stage1(luts, frames, out=feat))), flush=True)
     L.lerf_debug_lut_variant(1, 0)
+    if ONLY == "s1":
+        continue
     if ONLY != "prod":  # shared-memory carve-out of the production stage-1 kernel (percent of the unified L1 / shared memory)
         for pct in (0, 7, 14, 28, 50):
             L.lerf_debug_carveout(pct)

@@ -28,8 +28,9 @@ static int rhe_div(int num, int den) {
   return q;
 }
 
+// paired != 0 (oC = 1 only): two lookups per sorting network (simplex_pair_of), paired like lut_stage_cell_body does.
 extern "C" int emul_stage_cell(int stage, const int8_t* const* tables, int oC, const uint8_t* img, int P, int H, int W,
-                               int ha, int hb, int hc, uint8_t* out) {
+                               int ha, int hb, int hc, int paired, uint8_t* out) {
   const Hash h{(uint32_t)ha, (uint32_t)hb, (uint32_t)hc};
   const int ntab = stage == 1 ? 3 : 6;
   const size_t stride = oC == 3 ? 48 : 16;
@@ -45,13 +46,21 @@ extern "C" int emul_stage_cell(int stage, const int8_t* const* tables, int oC, c
         int n[3] = {0, 0, 0};
         for (int mode = 0; mode < 3; ++mode)
           for (int r = 0; r < 4; ++r) {
-            uint32_t xw[4];
-            for (int k = 0; k < 4; ++k) {
-              int dy, dx;
-              tap_offset(mode, r, k, dy, dx);
-              xw[k] = split_px(img[((size_t)p * H + clampi(y + dy, 0, H - 1)) * W + clampi(x + dx, 0, W - 1)]);
+            uint32_t xw[2][4];
+            for (int j = 0; j < 2; ++j)
+              for (int k = 0; k < 4; ++k) {
+                int dy, dx;
+                tap_offset(mode, (r & ~1) + j, k, dy, dx);
+                xw[j][k] = split_px(img[((size_t)p * H + clampi(y + dy, 0, H - 1)) * W + clampi(x + dx, 0, W - 1)]);
+              }
+            Simplex s;
+            if (paired && oC == 1) {
+              Simplex sp[2];
+              simplex_pair_of(xw[0], xw[1], h, sp[0], sp[1]);
+              s = sp[r & 1];
+            } else {
+              s = simplex_of(xw[r & 1][0], xw[r & 1][1], xw[r & 1][2], xw[r & 1][3], h);
             }
-            const Simplex s = simplex_of(xw[0], xw[1], xw[2], xw[3], h);
             const uint8_t* tab = packed[stage == 1 ? mode : 2 * mode + (r & 1)].data() + (size_t)s.cell * stride;
             for (int ch = 0; ch < oC; ++ch) {
               uint32_t q[4];

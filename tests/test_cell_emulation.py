@@ -29,14 +29,14 @@ def emul():
     return ctypes.CDLL(LIB)
 
 
-def _run(emul, stage, tables, oC, img_chw, hash_w=(9, 5, 3)):
+def _run(emul, stage, tables, oC, img_chw, hash_w=(9, 5, 3), paired=0):
     P, H, W = img_chw.shape
     tabs = [np.ascontiguousarray(t, dtype=np.int8) for t in tables]
     arr = (ctypes.c_void_p * len(tabs))(*[t.ctypes.data for t in tabs])
     out = np.empty((P * oC, H, W), dtype=np.uint8)
     img = np.ascontiguousarray(img_chw, dtype=np.uint8)
     assert emul.emul_stage_cell(stage, arr, oC, ctypes.c_void_p(img.ctypes.data), P, H, W,
-                                hash_w[0], hash_w[1], hash_w[2], ctypes.c_void_p(out.ctypes.data)) == 0
+                                hash_w[0], hash_w[1], hash_w[2], paired, ctypes.c_void_p(out.ctypes.data)) == 0
     return out
 
 
@@ -57,8 +57,9 @@ def test_cell_lookup_equals_oracle(emul, oC, kind):
     for m in "sct":
         t2 += [luts["s2_%sr0" % m], luts["s2_%sr1" % m]]
     for hw in ((9, 5, 3), (0, 0, 0), (7, 11, 13)):
-        assert np.array_equal(_run(emul, 1, t1, 1, chw, hw), feat), hw
-        assert np.array_equal(_run(emul, 2, t2, oC, feat, hw), codes), hw
+        for paired in (0, 1):  # 1: two lookups per 16x2 sorting network (the production form of the oC = 1 kernels)
+            assert np.array_equal(_run(emul, 1, t1, 1, chw, hw, paired), feat), (hw, paired)
+            assert np.array_equal(_run(emul, 2, t2, oC, feat, hw, paired), codes), (hw, paired)
 
 
 @pytest.mark.parametrize("kind", ["shipped", "random"])

@@ -121,10 +121,11 @@ def test_stage_kernel_variants_are_bitwise_identical(lp, oC):
     # (stage-1 variant, stage-2 variant), include/lerf_b200_testing.h.  Product library: the cell kernel and the
     # paired-window kernel are each other's second implementation for stage 2; a -DLERF_EXPERIMENTS build adds the
     # row-major kernel (1), cell tuning variants (22..25), the table-format mix (40..), the max-tap kernel (60..), the
-    # stage-1 window kernels (80.., cell pairs 90..).
-    pairs = [(0, 0), (0, 24), (0, 80)]
+    # stage-1 window kernels (80.., cell pairs 90..).  27 = the cell kernel with one sort per lookup (production sorts two
+    # lookups per 16x2 network).
+    pairs = [(0, 0), (0, 24), (0, 80), (27, 27)]
     if L.lerf_build_has_experiments():
-        pairs += [(1, 1), (22, 22), (23, 23), (25, 25), (80, 80), (81, 81), (90, 80), (91, 80), (92, 80)]
+        pairs += [(1, 1), (22, 22), (23, 23), (25, 25), (28, 24), (29, 24), (80, 80), (81, 81), (90, 80), (91, 80), (92, 80)]
         if oC == 3:
             pairs += [(0, v) for v in (40, 42, 44, 60, 61, 62, 63, 67, 69, 70, 72, 81, 82)]
         else:
