@@ -23,13 +23,24 @@ for model, linear in (("lerf-g", False), ("lerf-l", True)):
         lp.lib().lerf_debug_lut_variant(2, 80 if linear else 24)  # the other implementation
         assert torch.equal(lp.lut_stage2(luts, feat), codes)
         lp.lib().lerf_debug_lut_variant(2, 0)
-        for s in (2, 3, 4, 8, 2.5):
-            sr = lp.LerfSR(luts, s)
+        lp.lib().lerf_debug_lut_variant(1, 27)  # stage 1 with one sort per lookup against the paired 16x2 sort
+        assert torch.equal(lp.lut_stage1(luts, img), feat)
+        lp.lib().lerf_debug_lut_variant(1, 0)
+        for s in (2, 3, 4, 8, 2.5, 3.5, (3.3, 3.9)):
+            sr = lp.LerfSR(luts, *(s if isinstance(s, tuple) else (s,)))
             for fmt in ("f32", "u8", "u8_hwc"):
                 sr(img, out_format=fmt)
             oH = sr.out_sz[0]
             if oH >= 8:
                 sr(img, out_format="u8_hwc", rows=(3, oH - 2))
+        lp.lib().lerf_debug_force_generic(3)  # the any-scale cell kernel on a small scale as well
+        lp.LerfSR(luts, 1.5, 2.0)(img, out_format="u8_hwc")
+        lp.lib().lerf_debug_force_generic(0)
+        if h > 1:  # non-default operator parameters: the support kernels of resize and warp
+            lp.LerfSR(luts, 2.5, support_sz=4)(img, out_format="f32")
+            M = np.array([[1.3, 0.1, -2.0], [-0.05, 1.2, 1.0], [2e-4, -1e-4, 1.0]])
+            lp.LerfWarp(luts, support_sz=3, pad_mode="reflect")(img, M, (h + 9, w + 5), out_format="u8_hwc")
+            lp.LerfWarp(luts)(img, M, (h + 9, w + 5), out_format="f32")
     luts.close()
 ld = lp.load_lut_dict(util.lut_dir("lerf-g"))
 m = lp.LutFineTune(ld).cuda()
