@@ -4,6 +4,7 @@ import csv
 import sys
 
 rows = list(csv.reader(open(sys.argv[1])))
+MIN_US = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0  # only launches at least this long (the bench's 8-frame launches: 1000)
 h = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
 hdr = rows[h]
 ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
@@ -13,6 +14,8 @@ for r in rows[h + 1:]:
         continue
     v = float(r[vi].replace(",", ""))
     v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(r[ui], 1e-3)
+    if v < MIN_US:
+        continue
     n = r[ki].split("(")[0].replace("void ", "")
     a = agg.setdefault(n, [0, 0.0])
     a[0] += 1
