@@ -519,16 +519,22 @@ __device__ __forceinline__ void resize_int_u8_planar_body(const uint8_t* __restr
   const bool half = lead || trail, both = lead && trail;                      // 16-bit stores: lane 0 / a lane without partner
   const int off16 = col + (lead ? 0 : 2), sh16 = lead ? 0 : 16;
   const bool whole = valid && col >= 0 && col + S <= oW;                       // x8
+  // the cell's first row, once; row mr is a compile-time multiple of the pitch away (one 64-bit multiply-add per pointer and row
+  // instead of the full 64-bit row-index product: the kernel is issue-bound and this was 9 instructions per row)
+  unsigned char* const row0 = plane + (long long)(S * ly + g.ph_y) * oW;
+  unsigned char* const p_al = row0 + col + 2;
+  unsigned char* const p_16 = row0 + off16;
   gauss_cell_rowq<S, CG>(sm, g, tx, ty, S * ly + g.ph_y, oy0, oy1, [&](int mr, const uint32_t* res) {
-    unsigned char* row = plane + (long long)(S * ly + g.ph_y + mr) * oW;
+    const long long ro = (long long)mr * oW;
+    unsigned char* row = row0 + ro;
     if (S == 4) {
       const uint32_t w = pack4(res[0], res[1], res[2 % S], res[3 % S]);
       const uint32_t n = __shfl_down_sync(0xffffffffu, w, 1);
       uint32_t al;
       asm("prmt.b32 %0, %1, %2, 0x5432;" : "=r"(al) : "r"(w), "r"(n));
-      if (partner) __stcg(reinterpret_cast<uint32_t*>(row + col + 2), al);
-      if (half) __stcg(reinterpret_cast<unsigned short*>(row + off16), (unsigned short)(w >> sh16));
-      if (both) __stcg(reinterpret_cast<unsigned short*>(row + col + 2), (unsigned short)(w >> 16));  // a one-cell-wide block column
+      if (partner) __stcg(reinterpret_cast<uint32_t*>(p_al + ro), al);
+      if (half) __stcg(reinterpret_cast<unsigned short*>(p_16 + ro), (unsigned short)(w >> sh16));
+      if (both) __stcg(reinterpret_cast<unsigned short*>(p_al + ro), (unsigned short)(w >> 16));  // a one-cell-wide block column
     } else {
       const uint32_t w0 = pack4(res[0], res[1], res[2 % S], res[3 % S]), w1 = pack4(res[4 % S], res[5 % S], res[6 % S], res[7 % S]);
       if (whole) {
