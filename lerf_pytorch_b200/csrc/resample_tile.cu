@@ -7,8 +7,9 @@
 //   SteeringGaussianWarp2dNumpy.warp     :516-577   AmplifiedLinearWarp2dNumpy.warp     :597-635   geometry :292-407
 //
 // Same arithmetic as resample_int.cuh: per-tap coefficients are exact float64 promotions of the reference's float32
-// hyper values (per-code tables), the exponent is evaluated in float64 and rounded ONCE to unsigned fixed point
-// (magic-number add, magic last), the smallest of the four becomes weight 1, only differences go through ex2.approx, and
+// hyper values (per-code tables), the exponent is evaluated in float64 on top of the rounding constant of an unsigned
+// fixed point (SR kernels: column terms hoisted with the taps, the ROWQ order of resample_int.cuh, three roundings at the
+// fixed-point scale; warp: magic-number add last, one rounding), the smallest of the four becomes weight 1, only differences go through ex2.approx, and
 // the output is v0 + sum w_t (v_t - v0) / sum w_t with exact integer differences.  The exact-operation-order float64
 // kernels of resample.cu stay as the parity path (float32-hyper API, lerf_debug_force_generic).
 //
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(kOX* kTY)
   const int* lyp = left_y + oy;
   const double* dyp = dist_y + 2 * oy;
   int ly_cur = -1 << 30;
-  double ca[4], cb[4], cq[4];  // Gaussian: a', b', c' dc^2 per tap;  linear: ca = alpha
+  double ca[4], cb[4], cq[4];  // Gaussian: a', b' * -dc, magic + c' * -dc^2 per tap;  linear: ca = alpha
   float dv[4], v0 = 0.0f;
 #pragma unroll 1
   for (; oy <= oy_end; oy += row_step, ip += ip_step, ih += ih_step, lyp += row_step, dyp += 2 * row_step) {
@@ -163,9 +164,9 @@ __global__ void __launch_bounds__(kOX* kTY)
         for (int b = 0; b < 2; ++b) {  // patch order a*2+b as in the reference (:95-98)
           const int t = a * 2 + b;
           ca[t] = sm.sA[ly + b][lx + a];
-          if constexpr (KIND == LERF_KIND_GAUSS) {
-            cb[t] = sm.sB[ly + b][lx + a];
-            cq[t] = sm.sC[ly + b][lx + a] * ndc2[a];
+          if constexpr (KIND == LERF_KIND_GAUSS) {  // column terms hoisted with the taps (r2: the ROWQ form of resample_int.cuh)
+            cb[t] = sm.sB[ly + b][lx + a] * -dc[a];             // b' * -dc
+            cq[t] = fma(sm.sC[ly + b][lx + a], ndc2[a], fq.magic);  // magic + c' * -dc^2  (>= magic)
           }
           dv[t] = sm.sV[ly + b][lx + a];
         }
@@ -181,9 +182,9 @@ __global__ void __launch_bounds__(kOX* kTY)
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
           const int t = a * 2 + b;
-          double e = fma(ca[t], ndr2[b], cq[t]);
-          e = fma(cb[t], -(dr[b] * dc[a]), e);
-          q[t] = (unsigned)__double2loint(e + fq.magic);  // round(-log2 w * 2^FB) + 16
+          // the two non-negative terms first, the signed cross term last: no partial sum leaves magic's binade
+          const double e = fma(cb[t], dr[b], fma(ca[t], ndr2[b], cq[t]));
+          q[t] = (unsigned)__double2loint(e);  // round(-log2 w * 2^FB) + 16
         }
       res = combine_uq(q, dv, v0, fq.neg_scale);
     } else {
