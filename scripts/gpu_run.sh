@@ -6,7 +6,7 @@
 #   bench [N]             the driver's bench line at N GPUs (torchrun for N > 1) -> gpurun_out/bench_n<N>.json
 #   micro                 the gather micro-benchmarks (binaries built here by nvcc travel in build/)
 #   e2e [N]               host-to-host probe with every rank copying at once + the bench line at N
-#   sanitize              compute-sanitizer memcheck + racecheck over the r2 kernels on small inputs
+#   sanitize              compute-sanitizer memcheck / racecheck / initcheck / synccheck over the r2 kernels on small inputs
 #   final                 the evidence pass (tests, per-config table, bench + reference arm, ncu captures, launch list)
 set -u
 mkdir -p gpurun_out
@@ -29,7 +29,7 @@ case "$what" in
   e2e)
     N=${1:-8} bash scripts/gpu_e2e_probe.sh ;;
   sanitize)
-    for tool in memcheck racecheck; do
+    for tool in memcheck racecheck initcheck synccheck; do
       compute-sanitizer --tool $tool --error-exitcode 9 python scripts/sanitize_probe.py > gpurun_out/sanitizer_$tool.log 2>&1
       echo "$tool rc=$?"; tail -3 gpurun_out/sanitizer_$tool.log
     done ;;
