@@ -785,24 +785,24 @@ def test_run_host_equals_device_path(lp, luts, hw, scale):
 
 
 def test_randomised_parity_sweep(lp):
-    """scripts/fuzz_parity.py: random sizes (1..96 x 1..129), integer / near-integer / anisotropic / extreme scales, both
+    """tests/tools/fuzz_parity.py: random sizes (1..96 x 1..129), integer / near-integer / anisotropic / extreme scales, both
     models, all formats, random row bands, against the oracle.  30 cases here; 80 were run for profiles/r1e_fuzz_parity_tail.log."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_parity.py"), "30", "777"], capture_output=True,
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "tools", "fuzz_parity.py"), "30", "777"], capture_output=True,
                          text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert "all 30 cases within the parity bars" in out.stdout
 
 
 def test_randomised_warp_sweep(lp):
-    """scripts/fuzz_warp.py: random sizes and homographies (rotation, anisotropic scale 1..10, shear, perspective, canvases that
+    """tests/tools/fuzz_warp.py: random sizes and homographies (rotation, anisotropic scale 1..10, shear, perspective, canvases that
     cut the image), both models: mask identical, fp32 <= 1e-4 and uint8 <= 1 LSB inside the mask."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_warp.py"), "20", "99"], capture_output=True,
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "tools", "fuzz_warp.py"), "20", "99"], capture_output=True,
                          text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert "all 20 cases within the parity bars" in out.stdout

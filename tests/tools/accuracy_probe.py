@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """GPU box: max-abs / percentile error of the fp32 output against the float64 oracle on large frames.
-Usage: python scripts/accuracy_probe.py [rows]   (rows of a 2040-wide frame; default 1356 = full cfg-3 frame)"""
+Usage: python tests/tools/accuracy_probe.py [rows]   (rows of a 2040-wide frame; default 1356 = full cfg-3 frame)"""
 import os
 import sys
 import time
@@ -8,7 +8,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import lerf_pytorch_b200 as lp  # noqa: E402

@@ -3,7 +3,7 @@
 anisotropic, large), both models, all output formats, random row bands.  Prints one line per case and a summary; exit code 1
 on the first violation of the parity bars (stages bit-exact, fp32 <= 1e-4, uint8 <= 1 LSB, bands bit-identical).
 
-    python scripts/fuzz_parity.py [cases] [seed]
+    python tests/tools/fuzz_parity.py [cases] [seed]
 """
 import os
 import sys
@@ -11,7 +11,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import lerf_pytorch_b200 as lp  # noqa: E402

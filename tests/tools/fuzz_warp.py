@@ -3,7 +3,7 @@
 anisotropic scale 1..10, shear, perspective, canvases that cut the image), both models.  Bars: validity mask identical,
 fp32 <= 1e-4 and uint8 <= 1 LSB inside the mask.  Outside the mask (clipped taps) it only reports how far the two are apart.
 
-    python scripts/fuzz_warp.py [cases] [seed]
+    python tests/tools/fuzz_warp.py [cases] [seed]
 """
 import os
 import sys
@@ -11,7 +11,7 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import lerf_pytorch_b200 as lp  # noqa: E402
