@@ -202,6 +202,19 @@ int lerf_sr_fused(const lerf_luts_t* luts, int kind, const lerf_sr_plan_t* plan,
                   void* scratch, void* out, int out_format, lerf_stream_t stream);
 
 
+/* ---- result images as PNG files, on the device (output side) ---------------------------------
+ * Replaces the host-side `Image.fromarray(...).save(...)` of the result images (resample/eval_lut_sr.py:667-708,
+ * eval_lut_warp.py:224-262).  img: DEVICE uint8 [H][W][channels] (channels 1, 2, 3, 4 = grey, grey + alpha, RGB, RGBA),
+ * contiguous; png: DEVICE, 16-byte aligned, at least lerf_png_stored_bytes(...) rounded up to 4 bytes; scratch32: DEVICE, 32
+ * bytes, 8-byte aligned.  The file is a complete PNG with filter type 0 and STORED deflate blocks (lossless, no
+ * compression: H * (1 + W * channels) bytes of image data + 5 per 65535 + 63); Adler-32 and CRC-32 are computed on the
+ * device.  Copy lerf_png_stored_bytes(...) bytes to the host and write them to disk.  lerf_png_stored_bytes returns -1 for a
+ * bad shape or an image whose data does not fit one IDAT chunk (2^31 - 1 bytes). */
+long long lerf_png_stored_bytes(int H, int W, int channels);
+int lerf_png_encode_stored(const uint8_t* img, int H, int W, int channels, uint8_t* png, long long png_capacity, void* scratch32,
+                           lerf_stream_t stream);
+
+
 /* ---- LUT fine-tuning operators ---------------------------------------------------------------
  * Forward and backward of the two differentiable pieces the reference trains through when it fine-tunes its LUTs
  * (resample/train_model.py --lutft); float32 like its torch path.

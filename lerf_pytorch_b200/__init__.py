@@ -19,6 +19,7 @@ from .resize_right2d import (  # noqa: F401
 
 from . import metrics  # noqa: F401
 from .lut_finetune import LutFineTune, interp_torch_batch, steering_gaussian_resize  # noqa: F401
+from .png_gpu import encode_png, png_bytes, save_png  # noqa: F401
 from .sharding import band_halo_rows, band_input_rows, image_shard, row_bands  # noqa: F401
 
 __version__ = "0.1.0"

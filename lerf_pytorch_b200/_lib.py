@@ -45,6 +45,8 @@ PROTOTYPES = {
     "lerf_sr_scratch_bytes": (_c_sz, [_c_i, _c_i, _c_i, _c_i]),
     "lerf_sr_fused": (_c_i, [_c_p, _c_i, _c_p, _c_p, _c_i, _c_i, _c_ll, _c_ll, _c_ll, _c_ll, _c_f, _c_i, _c_i, _c_p,
                              _c_p, _c_i, _c_p]),
+    "lerf_png_stored_bytes": (_c_ll, [_c_i, _c_i, _c_i]),
+    "lerf_png_encode_stored": (_c_i, [_c_p, _c_i, _c_i, _c_i, _c_p, _c_ll, _c_p, _c_p]),
     "lerf_lut_ft_forward": (_c_i, [_c_p, _c_i, _c_p, _c_i, _c_i, _c_i, ctypes.c_char, _c_i, _c_p, _c_p]),
     "lerf_lut_ft_backward": (_c_i, [_c_p, _c_i, _c_p, _c_i, _c_i, _c_i, ctypes.c_char, _c_i, _c_p, _c_p]),
     "lerf_resize_sr_f32_backward": (_c_i, [_c_i, _c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_f, _c_p, _c_p, _c_p, _c_p, _c_p, _c_p]),

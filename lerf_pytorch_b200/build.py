@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "liblerf_b200.so")
 LIB_EXP = os.path.join(HERE, "liblerf_b200_exp.so")
 SOURCES = ["lut.cu", "lut_cell.cu", "lut_pw.cu", "resample.cu", "resample_int.cu", "resample_tile.cu", "warp_fixed.cu",
-           "fused.cu", "pipeline.cu", "lut_ft.cu"]
+           "fused.cu", "pipeline.cu", "lut_ft.cu", "png.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 

@@ -47,6 +47,9 @@ def build_parser(description, default_test_dir):
     p.add_argument('--gpu-metrics', dest='gpu_metrics', action='store_true', default=False,
                    help='compute PSNR-Y / SSIM / mPSNR on the device (metrics_gpu.py); with --no-save the result image never '
                         'leaves the GPU')
+    p.add_argument('--gpu-png', dest='gpu_png', action='store_true', default=False,
+                   help='write the result image with the device PNG writer (png_gpu.py: stored deflate blocks, lossless, '
+                        'uncompressed) instead of PIL on the host')
     p.add_argument('--io-threads', dest='io_threads', type=int, default=4,
                    help='host threads that decode the next images and encode / score finished ones while the GPU works '
                         '(SURVEY.md 8f item 2); 0 = everything inline like the reference')

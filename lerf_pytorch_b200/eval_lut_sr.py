@@ -82,19 +82,31 @@ class Evaluator(object):
                 gpu_score = metrics_gpu.psnr_y_ssim(torch.from_numpy(np.ascontiguousarray(img_gt)).to(self.device), d_out,
                                                     scale_h, scale_w)
             img_out = d_out.cpu().numpy() if (opt.save or gpu_score is None) else None
+            png_file = None
+            if opt.save and getattr(opt, "gpu_png", False):  # the PNG FILE of the result is assembled on the device
+                from . import png_gpu
+                png_file = png_gpu.encode_png(d_out).cpu().numpy()
             if opt.save:
                 feat, codes = sr.stages(d_in)
                 feat = feat.cpu().numpy()
                 img_hyper = codes.cpu().numpy().astype(np.float32) / float(255)  # :623-628
         if opt.save:
             stem = fname.split("/")[-1][:-4]
-            io.submit(_save_png, img_out, os.path.join(result_path, "{}_{}.png".format(stem, opt.lutName)))
+            if png_file is not None:
+                io.submit(_write_bytes, png_file, os.path.join(result_path, "{}_{}.png".format(stem, opt.lutName)))
+            else:
+                io.submit(_save_png, img_out, os.path.join(result_path, "{}_{}.png".format(stem, opt.lutName)))
             io.submit(_save_png, np.ascontiguousarray(feat.transpose((1, 2, 0))), os.path.join(result_path, "{}_lr.png".format(stem)))
             io.submit(_save_png, img_gt, os.path.join(result_path, "{}_gt.png".format(stem)))
             io.submit(np.save, os.path.join(result_path, "{}_{}_hyper.npy".format(fname.split("_")[-1][:-4], opt.lutName)), img_hyper)
         if gpu_score is not None:
             return io.submit(lambda: gpu_score)
         return io.submit(metrics.psnr_y_ssim, img_gt, img_out, scale_h, scale_w)
+
+
+def _write_bytes(arr, path):
+    with open(path, "wb") as f:
+        f.write(arr.tobytes())
 
 
 def _save_png(arr, path):

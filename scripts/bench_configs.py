@@ -171,6 +171,28 @@ def fixed():
                img.numel(), out.numel())
 
 
+def png():
+    """The device PNG writer (lerf_png_encode_stored) on result images of the benched sizes, against PIL on the host."""
+    import io
+    import time
+    from PIL import Image
+    for (h, w) in ((512, 512), (5424, 8160)):
+        img = natural(1, h, w, 6000)[0]
+        n = lp.png_bytes(h, w, 3)
+        buf = torch.empty((n + 3) & ~3, dtype=torch.uint8, device=dev)
+        lp.encode_png(img, out=buf)
+        ms = timeit(lambda: lp.encode_png(img, out=buf), 10)
+        host = torch.empty(n, dtype=torch.uint8).pin_memory()
+        ms_d2h = timeit(lambda: host.copy_(buf[:n], non_blocking=True), 5)
+        arr = img.cpu().numpy()
+        t0 = time.perf_counter()
+        Image.fromarray(arr).save(io.BytesIO(), format="PNG")
+        pil_ms = (time.perf_counter() - t0) * 1e3
+        print(json.dumps({"config": "png/%dx%d" % (w, h), "workload": "device PNG writer, stored deflate blocks, RGB", "ms": round(ms, 4),
+                          "file_MB": round(n / 1e6, 2), "image_GBps": round(img.numel() / ms / 1e6, 1), "d2h_ms": round(ms_d2h, 3),
+                          "pil_host_encode_ms": round(pil_ms, 1)}), flush=True)
+
+
 def cfg5():
     luts = lp.LutSet(lp.load_lut_dict(os.path.join(LUTS, "lerf-g")), device=dev)
     img = natural(1, 2160, 3840, 5000)[0]

@@ -48,3 +48,20 @@ def test_adapters_with_gpu_metrics_print_the_same_tables(tmp_path):
     lines, _ = eval_lut_warp.main(["-e", lut_dir("lerf-g"), "--testDir", os.path.join(DATA, "WarpBenchmark"), "--resultRoot",
                                    str(tmp_path), "--no-save", "--gpu-metrics"])
     assert lines[1].split("\t") == ["Set5".ljust(15, " ")] + WARP_PINS["lerf-g"]
+
+
+def test_sr_adapter_with_gpu_png_writes_the_same_images(tmp_path):
+    """--gpu-png: the result PNGs are assembled on the device (png_gpu.py); they decode to the pixels PIL's files hold and
+    the table does not change."""
+    import numpy as np
+    from PIL import Image
+    from lerf_pytorch_b200 import eval_lut_sr
+    base = ["-e", lut_dir("lerf-g"), "--testDir", os.path.join(DATA, "rrBenchmark")]
+    a, b = os.path.join(str(tmp_path), "pil"), os.path.join(str(tmp_path), "gpu")
+    lines_a, _ = eval_lut_sr.main(base + ["--resultRoot", a])
+    lines_b, _ = eval_lut_sr.main(base + ["--resultRoot", b, "--gpu-png"])
+    assert lines_a == lines_b
+    sub = os.path.join("lerf-g", "X4.00_4.00", "Set5")
+    for name in sorted(os.listdir(os.path.join(a, sub))):
+        if name.endswith("_LUTft.png"):
+            assert np.array_equal(np.asarray(Image.open(os.path.join(a, sub, name))), np.asarray(Image.open(os.path.join(b, sub, name)))), name
