@@ -62,13 +62,18 @@ class Evaluator(object):
             img_out = out.cpu().numpy()
             valid = mask.cpu().numpy().astype(bool)                        # mask_output == 255 (:229)
             feat = None
+            png_file = None
             if opt.save:
                 from .lut_interp import lut_stage1
                 feat = lut_stage1(self.luts, d_in, "HWC").cpu().numpy()
-        return io.submit(_score_and_save, img_out, img_gt, valid, feat, fname, result_path, opt.lutName, opt.save)
+                if getattr(opt, "gpu_png", False):  # non valid pixels white (:259-261), then the PNG file, both on the device
+                    from . import png_gpu
+                    shown = torch.where(mask.to(torch.bool).unsqueeze(-1), out, torch.full_like(out, 255))
+                    png_file = png_gpu.encode_png(shown).cpu().numpy()
+        return io.submit(_score_and_save, img_out, img_gt, valid, feat, fname, result_path, opt.lutName, opt.save, png_file)
 
 
-def _score_and_save(img_out, img_gt, valid, feat, fname, result_path, lut_name, save):
+def _score_and_save(img_out, img_gt, valid, feat, fname, result_path, lut_name, save, png_file=None):
     """Host side of eltr._worker after the warp (eval_lut_warp.py:226-261): mPSNR inside the mask, then the four PNGs."""
     from PIL import Image
     valid3 = np.repeat(valid[:, :, None], img_gt.shape[2], axis=2)
@@ -78,7 +83,11 @@ def _score_and_save(img_out, img_gt, valid, feat, fname, result_path, lut_name, 
         Image.fromarray(np.ascontiguousarray(feat.transpose((1, 2, 0)))).save(os.path.join(result_path, "{}_lr.png".format(stem)))
         Image.fromarray((valid3 * 255).astype(np.uint8)).save(os.path.join(result_path, "{}_mask.png".format(stem)))
         white = (np.ones_like(img_gt) * 255).astype(np.uint8)              # non valid pixels leave as white (:259-261)
-        Image.fromarray(img_out * valid3 + (~valid3) * white).save(os.path.join(result_path, "{}_{}.png".format(stem, lut_name)))
+        if png_file is not None:
+            with open(os.path.join(result_path, "{}_{}.png".format(stem, lut_name)), "wb") as f:
+                f.write(png_file.tobytes())
+        else:
+            Image.fromarray(img_out * valid3 + (~valid3) * white).save(os.path.join(result_path, "{}_{}.png".format(stem, lut_name)))
         Image.fromarray(img_gt * valid3 + (~valid3) * white).save(os.path.join(result_path, "{}_gt.png".format(stem)))
     return [mpsnr]
 

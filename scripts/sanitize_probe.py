@@ -42,6 +42,8 @@ for model, linear in (("lerf-g", False), ("lerf-l", True)):
             lp.LerfWarp(luts, support_sz=3, pad_mode="reflect")(img, M, (h + 9, w + 5), out_format="u8_hwc")
             lp.LerfWarp(luts)(img, M, (h + 9, w + 5), out_format="f32")
     luts.close()
+for shp in ((1, 1, 3), (37, 41, 3), (3, 21844, 3), (70, 33, 1)):  # device PNG writer: short, odd and block-boundary sizes
+    lp.encode_png(torch.randint(0, 256, shp, dtype=torch.uint8, device=dev))
 ld = lp.load_lut_dict(util.lut_dir("lerf-g"))
 m = lp.LutFineTune(ld).cuda()
 x = torch.rand((1, 1, 20, 18), device=dev)

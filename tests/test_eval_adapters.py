@@ -65,3 +65,23 @@ def test_sr_adapter_with_gpu_png_writes_the_same_images(tmp_path):
     for name in sorted(os.listdir(os.path.join(a, sub))):
         if name.endswith("_LUTft.png"):
             assert np.array_equal(np.asarray(Image.open(os.path.join(a, sub, name))), np.asarray(Image.open(os.path.join(b, sub, name)))), name
+
+
+def test_warp_adapter_with_gpu_png_writes_the_same_images(tmp_path):
+    """--gpu-png in the warp adapter: masking to white and the PNG file on the device; same pixels as PIL's files."""
+    import numpy as np
+    from PIL import Image
+    from lerf_pytorch_b200 import eval_lut_warp
+    base = ["-e", lut_dir("lerf-g"), "--testDir", os.path.join(DATA, "WarpBenchmark")]
+    a, b = os.path.join(str(tmp_path), "pil"), os.path.join(str(tmp_path), "gpu")
+    lines_a, _ = eval_lut_warp.main(base + ["--resultRoot", a])
+    lines_b, _ = eval_lut_warp.main(base + ["--resultRoot", b, "--gpu-png"])
+    assert lines_a == lines_b
+    n = 0
+    for root, _, files in os.walk(a):
+        for name in files:
+            if name.endswith("_LUTft.png"):
+                other = os.path.join(b, os.path.relpath(root, a), name)
+                assert np.array_equal(np.asarray(Image.open(os.path.join(root, name))), np.asarray(Image.open(other))), name
+                n += 1
+    assert n >= 2
