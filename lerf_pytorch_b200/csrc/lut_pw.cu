@@ -145,12 +145,12 @@ __device__ __forceinline__ void ld16(const uint8_t* p, uint32_t* q) {
 //   FmtCP:     "cell pair", oC = 1: the 16 corners of the cell for both orientations (2 x 16 bytes, lut_cell.cuh corner
 //              order) keyed by the cell alone -- 2 MiB per table, so neighbouring windows hit L1 like the per-pixel
 //              cell kernel does, but one sort and one 256-bit load serve two lookups.
-template <int OC>
+template <int OC, bool FOLD = false>
 struct FmtPW {
   using Lookup = pw::Lookup;
   static constexpr int nq = OC == 3 ? 8 : 4;
   static constexpr int kDefaultLD = 1;
-  __device__ static __forceinline__ Lookup prepare(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return pw::prepare(a, b, c, d); }
+  __device__ static __forceinline__ Lookup prepare(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return pw::prepare_t<FOLD>(a, b, c, d); }
   template <int LD>
   __device__ static __forceinline__ void fetch(const uint8_t* __restrict__ tab, const Lookup& L, uint32_t* q) {
     if (OC == 3) ld32<LD>(tab + (size_t)L.block * 32, q);
@@ -167,6 +167,11 @@ struct FmtPW {
       pw::blend1(q, L, n);
       o0.set(&n[0]);
       o1.set(&n[1]);
+    }
+    if (FOLD && L.flip) {  // the reversed window's block: its orientations are ours, swapped
+      const Pk<OC> t = o0;
+      o0 = o1;
+      o1 = t;
     }
   }
 };
@@ -414,7 +419,12 @@ constexpr size_t smem_bytes() { return (size_t)(8 * NJ + 2 * kHalo) * kPitch * 4
 // copies (family f reads table f >> 1) and the cell-pair tables.
 int build_pw_tables(lerf_luts_impl* L) {
   const int oC = L->oC2;
-  const size_t b2 = pw::table_bytes(oC);
+#ifdef LERF_EXPERIMENTS
+  constexpr int kPlanes = 64;  // the unfolded variants read every order plane
+#else
+  constexpr int kPlanes = 32;  // production reads folded: codes with t1 < 2 only (lut_pw.cuh prepare_t<true>)
+#endif
+  const size_t b2 = pw::table_bytes(oC, kPlanes);
 #ifdef LERF_EXPERIMENTS
   const size_t b1 = pw::table_bytes(1);
   const size_t off2 = 6 * b1;
@@ -425,7 +435,7 @@ int build_pw_tables(lerf_luts_impl* L) {
   cudaError_t e = cudaMalloc(&L->pw_block, total);
   if (e != cudaSuccess) return fail(LERF_ENOMEM, "cudaMalloc(%zu) for the paired-window LUT block failed: %s", total, cudaGetErrorString(e));
   L->pw_block_bytes = total;
-  dim3 grid(65536 / 256, 64);
+  dim3 grid(65536 / 256, kPlanes);
   for (int f = 0; f < 6; ++f) {
     uint8_t* d2 = (uint8_t*)L->pw_block + off2 + f * b2;
     // the row-major device copy of an oC = 3 table is padded to 4 bytes per entry
@@ -473,6 +483,8 @@ int launch_stage_pw(const lerf_luts_impl* L, int stage, const uint8_t* in, const
     pwk::lut_stage_pw_kernel<F, S, O, LD, B><<<grid, 256, pwk::smem_bytes<O>(), st>>>(t, in, ia, H, W, y0, y1, out); \
   }
   using pwk::FmtPW;
+  using PWF3 = pwk::FmtPW<3, true>;  // folded lookups (lut_pw.cuh prepare_t<true>): half the order planes are read
+  using PWF1 = pwk::FmtPW<1, true>;
   pwk::Tables t;
 #define LERF_GO_PIPE(B)                                                                                                       \
   {                                                                                                                            \
@@ -535,20 +547,22 @@ int launch_stage_pw(const lerf_luts_impl* L, int stage, const uint8_t* in, const
       case 6: LERF_GO_PIPE(1) break;
       case 7: LERF_GO_X6(4) break;
       case 8: LERF_GO_X6(3) break;
-      default: LERF_GO(FmtPW<3>, 2, 3, 1, 3)
+      case 9: LERF_GO(FmtPW<3>, 2, 3, 1, 3) break;  // unfolded lookups (r2a .. r2e production)
+      default: LERF_GO(PWF3, 2, 3, 1, 3)
     }
   } else {
     switch (variant) {
       case 1: LERF_GO(FmtPW<1>, 2, 1, 0, 3) break;
-      default: LERF_GO(FmtPW<1>, 2, 1, 1, 3)
+      case 9: LERF_GO(FmtPW<1>, 2, 1, 1, 3) break;
+      default: LERF_GO(PWF1, 2, 1, 1, 3)
     }
   }
 #else
   (void)variant;
   if (stage != 2) return fail(LERF_EUNSUPPORTED, "the window kernel serves stage 2 in this build");
   for (int i = 0; i < 6; ++i) t.t[i] = L->pw2[i];
-  if (L->oC2 == 3) LERF_GO(FmtPW<3>, 2, 3, 1, 3)
-  else LERF_GO(FmtPW<1>, 2, 1, 1, 3)
+  if (L->oC2 == 3) LERF_GO(PWF3, 2, 3, 1, 3)
+  else LERF_GO(PWF1, 2, 1, 1, 3)
 #endif
 #undef LERF_GO
 #undef LERF_GO_PIPE

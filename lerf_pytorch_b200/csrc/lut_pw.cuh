@@ -17,7 +17,8 @@
 //
 // Layout of one table ("plane-major"): byte offset = (code6 << 16 | cell) * B, B = 32 (oC = 3) or 16 (oC = 1);
 // code6 = t1 << 4 | t2 << 2 | t3 (the taps with the largest, 2nd and 3rd largest LSB; 24 of the 64 codes occur), so
-// every LSB order is one 2 MiB (1 MiB) plane and only 24 planes of a table are ever touched.
+// every LSB order is one 2 MiB (1 MiB) plane and only 24 planes of a table are ever touched -- 12 with the folded
+// lookup of production (prepare_t<true> below: t1 < 2, so the product library builds planes 0..31 only).
 //   oC = 3: word o*3 + ch = [P1..P4](o, ch);  word 6 + o = [P0(o,0), P0(o,1), P0(o,2), 0]
 //   oC = 1: word o = [P1..P4](o);  word 2 = [P0(0), P0(1), 0, 0];  word 3 = 0
 // Canonical tap order of a window: 2x2 block A B / C D -> (A, B, C, D); segments and diagonals from the anchor
@@ -56,10 +57,20 @@ struct Lookup {
   uint32_t block;  // code6 << 16 | cell: block index inside a table
   uint32_t wd;     // [f1-f2, f2-f3, f3-f4, f4]: byte weights of P1..P4
   uint32_t w0;     // 16 - f1: weight of P0
+  uint32_t flip;   // folded tables only: 1 = the block read is the REVERSED window's, its two orientations are swapped
 };
 
 // Taps in canonical order as cell::split_px words (lsb << 24 | msb << 8).
-LERF_HD Lookup prepare(uint32_t wa, uint32_t wb, uint32_t wc, uint32_t wd) {
+//
+// FOLD (r2): every family's two orientations read the window forwards and backwards (pi_of(f, 1, k) = pi_of(f, 0, 3 - k)),
+// so the block of window (p0, p1, p2, p3) with LSB order (t1, t2, t3, t4) is the block of the reversed window
+// (p3, p2, p1, p0) with order (3 - t1, ...) with its two orientations swapped.  Exactly one of the two has t1 < 2 (t1 = 3 - t1
+// has no solution), so only the 12 order planes with t1 in {0, 1} are ever read: half the table -- 72 instead of 144
+// 2-MiB pages for the six stage-2 tables, inside the 128-page TLB reach (profiles/r2a_tlbgather.csv), and 144 instead of
+// 288 MiB against the 126 MB L2 on inputs that scatter over the whole table.  Cost: the reversed cell index (three more
+// IMADs), two selects, and a swap of the two results.
+template <bool FOLD>
+LERF_HD Lookup prepare_t(uint32_t wa, uint32_t wb, uint32_t wc, uint32_t wd) {
   Lookup L;
   const uint32_t acc = ((wa * 16u + wb) * 16u + wc) * 16u + wd;  // bits 8..23 = cell (the lsb bytes land above)
   // key = lsb << 24 | msb << 8 | tap id: sorting descending orders the taps by lsb; ties (broken by msb, then id) may
@@ -72,8 +83,16 @@ LERF_HD Lookup prepare(uint32_t wa, uint32_t wb, uint32_t wc, uint32_t wd) {
   t = cell::imax(k2, k4); k4 = cell::imin(k2, k4); k2 = t;
   t = cell::imax(k2, k3); k3 = cell::imin(k2, k3); k2 = t;
   // bits 2..7 of the keys are zero, so the low six bits of k1*16 + k2*4 + k3 are (t1, t2, t3)
-  const uint32_t code = ((uint32_t)k1 * 16u + (uint32_t)k2 * 4u + (uint32_t)k3) & 0x3Fu;
-  L.block = (code << 16) | ((acc >> 8) & 0xFFFFu);
+  const uint32_t raw = (uint32_t)k1 * 16u + (uint32_t)k2 * 4u + (uint32_t)k3;
+  if (FOLD) {
+    const uint32_t accr = ((wd * 16u + wc) * 16u + wb) * 16u + wa;  // the reversed window's cell
+    L.flip = ((uint32_t)k1 >> 1) & 1u;                               // t1 >= 2
+    const uint32_t code = (raw ^ (0u - L.flip)) & 0x3Fu;             // 3 - t = t ^ 3 on every tap id
+    L.block = (code << 16) | (((L.flip ? accr : acc) >> 8) & 0xFFFFu);
+  } else {
+    L.flip = 0;
+    L.block = ((raw & 0x3Fu) << 16) | ((acc >> 8) & 0xFFFFu);
+  }
   const uint32_t f12 = prmt((uint32_t)k1, (uint32_t)k2, 0x0073u);  // [f1, f2, x, x]
   const uint32_t f34 = prmt((uint32_t)k3, (uint32_t)k4, 0x0073u);  // [f3, f4, x, x]
   const uint32_t F = prmt(f12, f34, 0x5410u);                      // [f1, f2, f3, f4]
@@ -81,6 +100,7 @@ LERF_HD Lookup prepare(uint32_t wa, uint32_t wb, uint32_t wc, uint32_t wd) {
   L.w0 = 16u - ((uint32_t)k1 >> 24);
   return L;
 }
+LERF_HD Lookup prepare(uint32_t wa, uint32_t wb, uint32_t wc, uint32_t wd) { return prepare_t<false>(wa, wb, wc, wd); }
 
 // oC = 3: q = the block's 8 words.  n[o][ch] += the lookup of orientation o.
 LERF_HD void blend3(const uint32_t q[8], const Lookup& L, int n[2][3]) {
@@ -105,7 +125,8 @@ LERF_HD void blend1(const uint32_t q[3], const Lookup& L, int n[2]) {
 #define LERF_HDC constexpr
 #endif
 LERF_HDC int block_bytes(int oC) { return oC == 3 ? 32 : 16; }
-LERF_HDC size_t table_bytes(int oC) { return (size_t)64 * 65536 * (size_t)(oC == 3 ? 32 : 16); }
+// `planes` order planes of 65536 blocks: 64 address every code6; folded lookups (prepare_t<true>) only read codes < 32.
+LERF_HDC size_t table_bytes(int oC, int planes = 64) { return (size_t)planes * 65536 * (size_t)(oC == 3 ? 32 : 16); }
 
 // Fills block (code6, cell) of family f from the row-major table T[17^4][entry_stride >= oC]; returns false (block untouched) for
 // the 40 codes that are not an order of four distinct taps.  Used by the repack kernel and by the CPU emulation.

@@ -45,7 +45,7 @@ for kind in os.environ.get("KB_KINDS", "natural,uniform").split(","):
         s1_variants = tuple(x for x in s1_variants if x[0] == 0 or x[0] >= 80)
     if ONLY == "s1":
         s1_variants = s1_variants[:4]
-    for v, name in (s1_variants[:1] if ONLY == "prod" else s1_variants):
+    for v, name in (s1_variants[:1] if ONLY in ("prod", "s2") else s1_variants):
         if ONLY == "s1" and v == 0:
             pass
         L.lerf_debug_lut_variant(1, v)
@@ -57,13 +57,22 @@ for kind in os.environ.get("KB_KINDS", "natural,uniform").split(","):
     L.lerf_debug_lut_variant(1, 0)
     if ONLY == "s1":
         continue
+    if ONLY == "s2":
+        codes = lp.lut_stage2(luts, ref_feat)
+        for v, name in ((0, "production (folded)"), (89, "pw unfolded lookups")):
+            L.lerf_debug_lut_variant(2, v)
+            c2 = lp.lut_stage2(luts, ref_feat)
+            assert torch.equal(c2, codes), "stage-2 variants disagree"
+            print("%-8s stage2 %-24s %8.1f us/frame" % (kind, name, timeit(lambda: lp.lut_stage2(luts, ref_feat, out=c2))), flush=True)
+        L.lerf_debug_lut_variant(2, 0)
+        continue
     if ONLY != "prod":  # shared-memory carve-out of the production stage-1 kernel (percent of the unified L1 / shared memory)
         for pct in (0, 7, 14, 28, 50):
             L.lerf_debug_carveout(pct)
             print("%-8s stage1 cell, carve-out %3d %%     %8.1f us/frame" % (kind, pct, timeit(lambda: lp.lut_stage1(luts, frames, out=feat))), flush=True)
         L.lerf_debug_carveout(-1)
     codes = lp.lut_stage2(luts, ref_feat)
-    s2_variants = ((0, "production (pw minb3)"), (70, "max-tap v10"), (1, "row-major minb4"), (23, "cell-48B minb3")) + tuple((60 + k, "max-tap v%d" % k) for k in range(13)) + ((42, "mix rm+max-tap 8/12"), (80, "pw minb3"), (81, "pw L1 minb3"), (82, "pw minb2"), (84, "pw pipelined minb2"), (85, "pw pipelined minb3"), (87, "pw 6-byte exchange minb4"), (88, "pw 6-byte exchange minb3"))
+    s2_variants = ((0, "production (pw minb3)"), (70, "max-tap v10"), (1, "row-major minb4"), (23, "cell-48B minb3")) + tuple((60 + k, "max-tap v%d" % k) for k in range(13)) + ((42, "mix rm+max-tap 8/12"), (80, "pw minb3"), (81, "pw L1 minb3"), (82, "pw minb2"), (84, "pw pipelined minb2"), (85, "pw pipelined minb3"), (87, "pw 6-byte exchange minb4"), (88, "pw 6-byte exchange minb3"), (89, "pw unfolded lookups"))
     if ONLY == "pw":
         s2_variants = tuple(x for x in s2_variants if x[0] in (0, 70) or x[0] >= 80)
     for v, name in (s2_variants[:1] if ONLY == "prod" else s2_variants):

@@ -152,8 +152,9 @@ extern "C" int emul_stage2_maxtap1(const int8_t* const* tables, const uint8_t* i
 // walked window by window over the whole (edge-replicated) image like lut_stage_pw_kernel does per tile.
 #include "../../lerf_pytorch_b200/csrc/lut_pw.cuh"
 
+// fold != 0: folded tables (prepare_t<true>: only order planes with t1 < 2 are read, results swapped on a flipped lookup).
 extern "C" int emul_stage_pw(int stage, const int8_t* const* tables, int oC, const uint8_t* img, int P, int H, int W,
-                             uint8_t* out) {
+                             int fold, uint8_t* out) {
   namespace pw = lerf::pw;
   static const int dest[6][2][2] = {{{0, 0}, {1, 1}}, {{1, 0}, {0, 1}}, {{0, 0}, {3, 0}},
                                     {{0, 0}, {0, 3}}, {{0, 0}, {3, 3}}, {{0, 0}, {-3, 3}}};  // [family][orientation](dx, dy)
@@ -169,7 +170,8 @@ extern "C" int emul_stage_pw(int stage, const int8_t* const* tables, int oC, con
             pw::window_tap(f, k, dx, dy);
             w[k] = split_px(img[((size_t)p * H + clampi(ay + dy, 0, H - 1)) * W + clampi(ax + dx, 0, W - 1)]);
           }
-          const pw::Lookup L = pw::prepare(w[0], w[1], w[2], w[3]);
+          const pw::Lookup L = fold ? pw::prepare_t<true>(w[0], w[1], w[2], w[3]) : pw::prepare(w[0], w[1], w[2], w[3]);
+          if (fold && ((L.block >> 20) & 3u) >= 2u) return 2;  // a folded lookup must stay in the planes with t1 < 2
           uint8_t blk[32];
           if (!pw::fill_block(T, oC, oC, f, L.block & 0xFFFFu, L.block >> 16, blk)) return 1;  // an impossible order code
           uint32_t q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -186,7 +188,7 @@ extern "C" int emul_stage_pw(int stage, const int8_t* const* tables, int oC, con
           for (int o = 0; o < 2; ++o) {
             const int x = ax + dest[f][o][0], y = ay + dest[f][o][1];
             if (x < 0 || x >= W || y < 0 || y >= H) continue;
-            for (int ch = 0; ch < oC; ++ch) acc[(((size_t)p * oC + ch) * H + y) * W + x] += n[o][ch];
+            for (int ch = 0; ch < oC; ++ch) acc[(((size_t)p * oC + ch) * H + y) * W + x] += n[o ^ (int)L.flip][ch];
           }
         }
     }

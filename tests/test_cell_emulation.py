@@ -104,14 +104,15 @@ def test_paired_window_lookup_equals_oracle(emul, oC, kind):
     for m in "sct":
         t2 += [luts["s2_%sr0" % m], luts["s2_%sr1" % m]]
 
-    def run(stage, tables, oc, src):
+    def run(stage, tables, oc, src, fold=0):
         tabs = [np.ascontiguousarray(t, dtype=np.int8) for t in tables]
         arr = (ctypes.c_void_p * len(tabs))(*[t.ctypes.data for t in tabs])
         out = np.empty((src.shape[0] * oc, src.shape[1], src.shape[2]), dtype=np.uint8)
         s = np.ascontiguousarray(src)
         assert emul.emul_stage_pw(stage, arr, oc, ctypes.c_void_p(s.ctypes.data), s.shape[0], s.shape[1], s.shape[2],
-                                  ctypes.c_void_p(out.ctypes.data)) == 0
+                                  fold, ctypes.c_void_p(out.ctypes.data)) == 0
         return out
 
-    assert np.array_equal(run(1, t1, 1, chw), feat)
-    assert np.array_equal(run(2, t2, oC, feat), codes)
+    for fold in (0, 1):  # 1: folded tables (half the order planes, results swapped on a reversed lookup)
+        assert np.array_equal(run(1, t1, 1, chw, fold), feat), fold
+        assert np.array_equal(run(2, t2, oC, feat, fold), codes), fold
