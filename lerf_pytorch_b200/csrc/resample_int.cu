@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kCX* kCY, MINB)
 }
 
 // uint8 outputs through a staged tile (resample_int.cuh): CH = 1 planar, CH = 3 interleaved
-template <int S, int CH, bool CG, bool TMA = true>
+template <int S, int CH, int CG, bool TMA = true>
 __global__ void __launch_bounds__(kCX* kCY, 4)
     resize_sr_int_gauss_u8_kernel(const uint8_t* __restrict__ feat, const uint8_t* __restrict__ codes, int H, int W, int oH,
                                   int oW, const __grid_constant__ IntGeom<S> g, const CoefTabs* __restrict__ ct, int ly0,
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(kCX* kCY, 4)
   resize_int_u8_body<S, CH, CG, TMA>(feat, codes, H, W, oH, oW, g, ct, ly0, oy0, oy1, out, blockIdx.x, blockIdx.y, blockIdx.z, sm, ot);
 }
 
-template <int S, bool CG>
+template <int S, int CG>
 __global__ void __launch_bounds__(kCX* kCY, 4)
     resize_sr_int_gauss_u8p_kernel(const uint8_t* __restrict__ feat, const uint8_t* __restrict__ codes, int H, int W, int oH,
                                    int oW, const __grid_constant__ IntGeom<S> g, const CoefTabs* __restrict__ ct, int ly0,
@@ -78,29 +78,37 @@ static int launch_int(const lerf_sr_plan_impl* P, const uint8_t* feat, const uin
 #ifdef LERF_EXPERIMENTS
   const int rv = g_dbg.resize_variant == 12 ? 11 : g_dbg.resize_variant;
 #else
-  const int rv = g_dbg.resize_variant == 11 || g_dbg.resize_variant == 12 ? 11 : 0;  // 11: geometry from kernel parameters (the flavour of odd scales); 12: 11 + HWC tile copied out by lanes instead of bulk stores
+  // 11: geometry from kernel parameters (the flavour of odd scales); 12: 11 + HWC tile copied out by lanes instead of bulk
+  // stores; 7 / 13: weights relative to the phase's nearest tap / to the smallest exponent (one of them is production)
+  const int rv = g_dbg.resize_variant == 11 || g_dbg.resize_variant == 12 ? 11 : (g_dbg.resize_variant == 7 || g_dbg.resize_variant == 13 ? g_dbg.resize_variant : 0);
 #endif
-  const IntGeom<S> g = make_geom<S>(P, max_sigma, /*unsigned_form=*/rv == 0 || rv == 4 || rv == 11);
+  const bool prod = rv == 0 || rv == 7 || rv == 13;
+  const bool cg = prod && geom_is_constexpr<S>(P);  // geometry factors as immediates (resample_int.cuh CGeom)
+  const bool ref = cg && (rv == 7 || (rv == 0 && kRefTapDefault));  // weights relative to the nearest tap (combine_ref)
+  const IntGeom<S> g = make_geom<S>(P, max_sigma, /*unsigned_form=*/prod || rv == 4 || rv == 11, /*signed_diff=*/ref);
   const CoefTabs* ct = plan_coef_tabs(P, max_sigma, st);
   if (!ct) return fail(LERF_ECUDA, "uploading the hyper decode tables failed");
   // cell rows touched by the output band
   const int ly0 = P->h_left_y[oy0], ly1 = P->h_left_y[oy1 - 1];
   dim3 block(kCX * kCY), grid((P->W + 1 + kCX - 1) / kCX, (ly1 - ly0 + 1 + kCY - 1) / kCY, planes);
-  const bool cg = rv == 0 && geom_is_constexpr<S>(P);  // geometry factors as immediates (resample_int.cuh CGeom)
+#define LERF_U8P(CGV) resize_sr_int_gauss_u8p_kernel<S, CGV><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, ly0, oy0, oy1, (unsigned char*)out)
+#define LERF_U8T(CHV, CGV) resize_sr_int_gauss_u8_kernel<S, CHV, CGV><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, ly0, oy0, oy1, (unsigned char*)out)
   // staged uint8 epilogue: the tile must fit the 48 KiB of static shared memory next to the coefficient tiles
-  if (g_dbg.u8_staged && (rv == 0 || rv == 11)) {
+  if (g_dbg.u8_staged && (prod || rv == 11)) {
     if constexpr (S == 4 || S == 8) {  // planar: aligned words through a lane shuffle (x4) or as they are (x8)
       if (fmt == LERF_OUT_U8 && g.ph_x == S / 2 && P->oW % 4 == 0 && ((uintptr_t)out & 3) == 0) {
-        if (cg) resize_sr_int_gauss_u8p_kernel<S, true><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, ly0, oy0, oy1, (unsigned char*)out);
-        else resize_sr_int_gauss_u8p_kernel<S, false><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, ly0, oy0, oy1, (unsigned char*)out);
+        if (ref) LERF_U8P(2);
+        else if (cg) LERF_U8P(1);
+        else LERF_U8P(0);
         LERF_LAUNCHED();
         return LERF_OK;
       }
     }
     if constexpr (S != 4 && S != 8) {  // planar at x2 / x3: the staged tile
       if (fmt == LERF_OUT_U8) {
-        if (cg) resize_sr_int_gauss_u8_kernel<S, 1, true><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, ly0, oy0, oy1, (unsigned char*)out);
-        else resize_sr_int_gauss_u8_kernel<S, 1, false><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, ly0, oy0, oy1, (unsigned char*)out);
+        if (ref) LERF_U8T(1, 2);
+        else if (cg) LERF_U8T(1, 1);
+        else LERF_U8T(1, 0);
         LERF_LAUNCHED();
         return LERF_OK;
       }
@@ -108,14 +116,17 @@ static int launch_int(const lerf_sr_plan_impl* P, const uint8_t* feat, const uin
     if constexpr (sizeof(OutTile<S, 3>) + sizeof(Smem) <= 48 * 1024) {
       if (fmt == LERF_OUT_U8_HWC && channels == 3 && planes % 3 == 0) {
         grid.z = planes / 3;
-        if (g_dbg.resize_variant == 12) resize_sr_int_gauss_u8_kernel<S, 3, false, false><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, ly0, oy0, oy1, (unsigned char*)out);
-        else if (cg) resize_sr_int_gauss_u8_kernel<S, 3, true><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, ly0, oy0, oy1, (unsigned char*)out);
-        else resize_sr_int_gauss_u8_kernel<S, 3, false><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, ly0, oy0, oy1, (unsigned char*)out);
+        if (g_dbg.resize_variant == 12) resize_sr_int_gauss_u8_kernel<S, 3, 0, false><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, ly0, oy0, oy1, (unsigned char*)out);
+        else if (ref) LERF_U8T(3, 2);
+        else if (cg) LERF_U8T(3, 1);
+        else LERF_U8T(3, 0);
         LERF_LAUNCHED();
         return LERF_OK;
       }
     }
   }
+#undef LERF_U8P
+#undef LERF_U8T
 #define LERF_GK(F, HO, B)                                                                                              \
   resize_sr_int_gauss_kernel<S, F, HO, B><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, \
                                                                   channels, ly0, oy0, oy1, out)
@@ -125,11 +136,13 @@ static int launch_int(const lerf_sr_plan_impl* P, const uint8_t* feat, const uin
   else if (g_dbg.resize_variant == 2) LERF_GK(F, 0, 4);         \
   else if (g_dbg.resize_variant == 5) LERF_GK(F, 0, 5);         \
   else if (g_dbg.resize_variant == 4) LERF_GK(F, 2, 5);         \
+  else if (ref) LERF_GK(F, 5, 4);                               \
   else if (cg) LERF_GK(F, 3, 4);                                \
   else LERF_GK(F, 2, 4)
 #else
 #define LERF_GO(F)               \
-  if (cg) LERF_GK(F, 3, 4);      \
+  if (ref) LERF_GK(F, 5, 4);     \
+  else if (cg) LERF_GK(F, 3, 4); \
   else LERF_GK(F, 2, 4)
 #endif
   switch (fmt) {

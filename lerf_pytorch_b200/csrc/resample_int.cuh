@@ -130,6 +130,51 @@ __device__ __forceinline__ float combine_uq(const unsigned q[4], const float dv[
   return v0 + qn;
 }
 
+// combine_uq with a FIXED reference tap R instead of the smallest exponent (r2): for a compile-time phase the nearest tap is
+// known, its distances are <= 1/2 per axis, so its -log2 w is at most L/2 (sigma (1/2 + 1/2))^2 = 72 for sigma = 10 and the
+// other weights, taken relative to it, stay below 2^72 -- far inside float32 -- while the reference weight is exactly 1: no
+// minimum (two VIMNMX3) and one tap's subtract / convert / scale / ex2 less per output sample.  The differences are SIGNED
+// now, so the plan's fixed point keeps one bit less (make_geom signed_diff: bound * 2^FB < 2^31).
+constexpr bool kRefTapDefault = true;  // production of the integer-scale kernels since r2h: 258 -> 234 us per 2K frame (float32)
+
+template <int R>
+__device__ __forceinline__ void weights_ref(const unsigned q[4], float neg_scale, float w[4]) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    if (t == R) {
+      w[t] = 1.0f;
+    } else {
+      const float x = __int2float_rn((int)(q[t] - q[R])) * neg_scale;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w[t]) : "f"(x));
+    }
+  }
+}
+template <int R>
+__device__ __forceinline__ float combine_ref(const unsigned q[4], const float dv[4], float v0, float neg_scale) {
+  float w[4];
+  weights_ref<R>(q, neg_scale, w);
+  const float den = (w[0] + w[1]) + (w[2] + w[3]);
+  const float num = fmaf(w[1], dv[1], fmaf(w[2], dv[2], w[3] * dv[3]));
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
+  float qn = num * r;
+  qn = fmaf(fmaf(-den, qn, num), r, qn);
+  return v0 + qn;
+}
+
+template <int R>  // uint8 flavour, see combine_uq_u8
+__device__ __forceinline__ uint32_t combine_ref_u8(const unsigned q[4], const float dv[4], float v0m, float neg_scale) {
+  float w[4];
+  weights_ref<R>(q, neg_scale, w);
+  const float den = (w[0] + w[1]) + (w[2] + w[3]);
+  const float num = fmaf(w[1], dv[1], fmaf(w[2], dv[2], w[3] * dv[3]));
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(den));
+  float qn = num * r;
+  qn = fmaf(fmaf(-den, qn, num), r, qn);
+  return __float_as_uint(v0m + qn);
+}
+
 // 1.5 * 2^23: adding it to a value in [0, 2^22) leaves round_half_even(value) in the low mantissa bits.
 constexpr float kRoundMagic = 12582912.0f;
 
@@ -208,8 +253,9 @@ __device__ __forceinline__ void resize_int_body(const uint8_t* __restrict__ feat
   long long rowh = ((long long)(p / channels) * oH + oyb) * oW;     // same for the interleaved layout
   const bool full = oxb >= 0 && oxb + S <= oW;
   constexpr bool kHoist = MODE == 1 && S <= 4;
-  constexpr bool kRowQ = MODE == 2 || MODE == 3;  // S = 8 would need 64 registers for the column terms
-  constexpr bool kCG = MODE == 3;                 // geometry factors as immediates (CGeom)
+  constexpr bool kRowQ = MODE == 2 || MODE == 3 || MODE == 5;  // S = 8 would need 64 registers for the column terms
+  constexpr bool kCG = MODE == 3 || MODE == 5;                 // geometry factors as immediates (CGeom)
+  constexpr bool kRef = MODE == 5;                             // weights relative to the phase's nearest tap (combine_ref)
   double colq[kHoist ? 4 : 1][kHoist ? S : 1];
   if (kHoist) {
 #pragma unroll
@@ -258,7 +304,16 @@ __device__ __forceinline__ void resize_int_body(const uint8_t* __restrict__ feat
       }
       if (kRowQ) {
         const unsigned uq[4] = {(unsigned)q[0], (unsigned)q[1], (unsigned)q[2], (unsigned)q[3]};
-        if (FMT == LERF_OUT_F32) res[mc] = combine_uq(uq, dv, v0, g.inv_scale);
+        if (FMT == LERF_OUT_F32 && kRef) {  // CGeom phases: tap (a, b) = (mc >= S/2, mr >= S/2) is the nearest one
+          if (mc * 2 >= S) res[mc] = mr * 2 >= S ? combine_ref<3>(uq, dv, v0, g.inv_scale) : combine_ref<2>(uq, dv, v0, g.inv_scale);
+          else res[mc] = mr * 2 >= S ? combine_ref<1>(uq, dv, v0, g.inv_scale) : combine_ref<0>(uq, dv, v0, g.inv_scale);
+        } else if (kRef) {  // uint8 formats that do not take a staged kernel (x8 interleaved): the same weights
+          const float v0m = v0 + kRoundMagic;
+          uint32_t bits;
+          if (mc * 2 >= S) bits = mr * 2 >= S ? combine_ref_u8<3>(uq, dv, v0m, g.inv_scale) : combine_ref_u8<2>(uq, dv, v0m, g.inv_scale);
+          else bits = mr * 2 >= S ? combine_ref_u8<1>(uq, dv, v0m, g.inv_scale) : combine_ref_u8<0>(uq, dv, v0m, g.inv_scale);
+          res[mc] = (float)(bits & 255u);
+        } else if (FMT == LERF_OUT_F32) res[mc] = combine_uq(uq, dv, v0, g.inv_scale);
         else res[mc] = (float)(combine_uq_u8(uq, dv, v0 + kRoundMagic, g.inv_scale) & 255u);  // one rounding, like every uint8 epilogue (r2)
       } else {
         res[mc] = combine_q(q, dv, v0, g.inv_scale);
@@ -319,7 +374,9 @@ __device__ __forceinline__ uint32_t to_u8_sat(float v) {  // clip(round_half_eve
 
 // The ROWQ arithmetic of resize_int_body for one cell: `emit(mr, res)` receives the S samples of output row oyb + mr.
 // (uint8 flavour: res[mc] carries the rounded sample in its low byte, see combine_uq_u8.)
-template <int S, bool CG, typename Emit>
+// CG: 0 = geometry factors from the kernel parameters, 1 = immediates (CGeom), 2 = immediates + weights relative to the
+// phase's nearest tap (combine_ref_u8).
+template <int S, int CG, typename Emit>
 __device__ __forceinline__ void gauss_cell_rowq(const Smem& sm, const IntGeom<S>& g, int tx, int ty, int oyb, int oy0, int oy1,
                                                 Emit emit) {
   double ca[4], cb[4], cc[4];
@@ -342,18 +399,23 @@ __device__ __forceinline__ void gauss_cell_rowq(const Smem& sm, const IntGeom<S>
     if (oy < oy0 || oy >= oy1) continue;
     double rowa[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) rowa[t] = fma(ca[t], geom_xr<S, CG>(g, mr, t & 1), g.magic);
+    for (int t = 0; t < 4; ++t) rowa[t] = fma(ca[t], geom_xr<S, CG != 0>(g, mr, t & 1), g.magic);
     uint32_t res[S];
 #pragma unroll
     for (int mc = 0; mc < S; ++mc) {
       unsigned uq[4];
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        double e = fma(cc[t], geom_xc<S, CG>(g, mc, t >> 1), rowa[t]);
-        e = fma(cb[t], geom_pp<S, CG>(g, mr, mc, t & 1, t >> 1), e);
+        double e = fma(cc[t], geom_xc<S, CG != 0>(g, mc, t >> 1), rowa[t]);
+        e = fma(cb[t], geom_pp<S, CG != 0>(g, mr, mc, t & 1, t >> 1), e);
         uq[t] = (unsigned)__double2loint(e);
       }
-      res[mc] = combine_uq_u8(uq, dv, v0m, g.inv_scale);
+      if (CG == 2) {  // CGeom phases: tap (a, b) = (mc >= S/2, mr >= S/2) is the nearest one
+        if (mc * 2 >= S) res[mc] = mr * 2 >= S ? combine_ref_u8<3>(uq, dv, v0m, g.inv_scale) : combine_ref_u8<2>(uq, dv, v0m, g.inv_scale);
+        else res[mc] = mr * 2 >= S ? combine_ref_u8<1>(uq, dv, v0m, g.inv_scale) : combine_ref_u8<0>(uq, dv, v0m, g.inv_scale);
+      } else {
+        res[mc] = combine_uq_u8(uq, dv, v0m, g.inv_scale);
+      }
     }
     emit(mr, res);
   }
@@ -419,7 +481,7 @@ __device__ __forceinline__ void copy_tile_out(const OutTile<S, CH>& ot, unsigned
 // uint8 outputs of the integer-scale Gaussian resampler through a staged tile.  CH = 1: planar [P][oH][oW], one plane per
 // block (blockIdx.z = plane).  CH = 3: interleaved [B][oH][oW][3], one image per block (blockIdx.z = batch index), the
 // three colour planes one after the other.
-template <int S, int CH, bool CG, bool TMA = true>
+template <int S, int CH, int CG, bool TMA = true>
 __device__ __forceinline__ void resize_int_u8_body(const uint8_t* __restrict__ feat, const uint8_t* __restrict__ codes, int H, int W,
                                                    int oH, int oW, const IntGeom<S>& g, const CoefTabs* __restrict__ ct, int ly0,
                                                    int oy0, int oy1, unsigned char* __restrict__ out, int bxi, int byi, int bz,
@@ -494,7 +556,7 @@ __device__ __forceinline__ void resize_int_u8_body(const uint8_t* __restrict__ f
 // bytes straddle an aligned word, so every lane takes the two leading bytes of its right-hand neighbour (one shuffle,
 // one PRMT) and stores the ALIGNED word 4*lx + 4 .. 4*lx + 7; only lane 0 (two leading bytes) and the last lane of a warp or
 // of the image (two trailing bytes) store bytes.  A x8 cell starts at 8*lx + 4 and stores two aligned words as they are.
-template <int S, bool CG>
+template <int S, int CG>
 __device__ __forceinline__ void resize_int_u8_planar_body(const uint8_t* __restrict__ feat, const uint8_t* __restrict__ codes, int H,
                                                           int W, int oH, int oW, const IntGeom<S>& g, const CoefTabs* __restrict__ ct,
                                                           int ly0, int oy0, int oy1, unsigned char* __restrict__ out, int bxi, int byi,
@@ -564,7 +626,7 @@ inline void make_coef_tabs(float max_sigma, CoefTabs& t) {
 
 // unsigned_form: constants for resize_int_body MODE 2 (negated geometry, magic = 2^(52-FB) + 16 units, inv_scale < 0).
 template <int S>
-inline IntGeom<S> make_geom(const lerf_sr_plan_impl* P, float max_sigma, bool unsigned_form = false) {
+inline IntGeom<S> make_geom(const lerf_sr_plan_impl* P, float max_sigma, bool unsigned_form = false, bool signed_diff = false) {
   IntGeom<S> g;
   double dmax_y = 0.0, dmax_x = 0.0;
   for (int m = 0; m < S; ++m)
@@ -586,7 +648,7 @@ inline IntGeom<S> make_geom(const lerf_sr_plan_impl* P, float max_sigma, bool un
   const double bound = 0.5 * kLog2e * reach * reach + 2.0;
   if (unsigned_form) {
     int fb = 26;
-    while (fb > 8 && bound * (double)(1u << fb) >= 4294967000.0) --fb;
+    while (fb > 8 && bound * (double)(1u << fb) >= (signed_diff ? 2147483000.0 : 4294967000.0)) --fb;
     g.magic = (double)(1ull << (52 - fb)) + 16.0 / (double)(1u << fb);
     g.inv_scale = -1.0f / (float)(1u << fb);
     for (int m = 0; m < S; ++m)

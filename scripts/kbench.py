@@ -115,6 +115,15 @@ for kind in os.environ.get("KB_KINDS", "natural,uniform").split(","):
             o2 = rs.resize_codes(ref_feat, codes, out_format=fmt)
             assert torch.equal(o2, out), "compile-time geometry changes the result"
             print("%-8s resize %-20s %8.1f us/frame" % (kind, "int-scale f32 r1 geom", timeit(lambda: rs.resize_codes(ref_feat, codes, out_format=fmt, out=o2))), flush=True)
+            L.lerf_debug_resize_variant(13)  # weights relative to the smallest exponent (production until r2g)
+            o2 = rs.resize_codes(ref_feat, codes, out_format=fmt)
+            print("%-8s resize %-20s %8.1f us/frame   max |diff to production| %.3g" % (kind, "int-scale f32 min-tap", timeit(lambda: rs.resize_codes(ref_feat, codes, out_format=fmt, out=o2)), float((o2 - out).abs().max())), flush=True)
+            L.lerf_debug_resize_variant(0)
+        if fmt != "f32":  # weights relative to the smallest exponent, uint8 flavours
+            L.lerf_debug_resize_variant(13)
+            o2 = rs.resize_codes(ref_feat, codes, out_format=fmt)
+            d = (o2.int() - out.int()).abs()
+            print("%-8s resize %-20s %8.1f us/frame   max LSB diff to production %d, differing %.2e" % (kind, "int-scale " + fmt + " min-tap", timeit(lambda: rs.resize_codes(ref_feat, codes, out_format=fmt, out=o2)), int(d.max()), float((d > 0).float().mean())), flush=True)
             L.lerf_debug_resize_variant(0)
         if fmt != "f32":  # the byte-store epilogue of r1 against the staged tile
             L.lerf_debug_resize_variant(10)

@@ -364,15 +364,17 @@ def test_pipeline_kernel_equals_three_launches(lp, luts, fmt):
         L.lerf_debug_pipeline(0, 4, 0)
 
 
-def test_resize_kernel_variants_within_tolerance(lp, orc, luts):
+@pytest.mark.parametrize("S", [4, 2, 8])
+def test_resize_kernel_variants_within_tolerance(lp, orc, luts, S):
     ld, ls = luts["g"]
-    img = uniform_image(61, 50, 47)
-    ref, _, _ = orc.lerf_sr(img, ld, 4, 4, linear=False)
-    sr = lp.LerfSR(ls, 4)
+    img = uniform_image(61 + S, 50, 47)
+    ref, _, _ = orc.lerf_sr(img, ld, S, S, linear=False)
+    sr = lp.LerfSR(ls, S)
     L = lp.lib()
     try:
         want = orc.to_uint8_hwc(ref)
-        for v in (0, 10, 11, 12) + ((1, 2, 4, 5) if L.lerf_build_has_experiments() else ()):
+        # 0 = production (weights relative to the phase's nearest tap), 13 = relative to the smallest exponent, 7 = 0 spelled out
+        for v in (0, 7, 13, 10, 11, 12) + ((1, 2, 4, 5) if L.lerf_build_has_experiments() else ()):
             L.lerf_debug_resize_variant(v)
             out = sr(_cuda(img), out_format="f32").cpu().numpy().astype(np.float64)
             print("resize variant %d: max-abs err %.3g" % (v, _maxabs(out, ref)))

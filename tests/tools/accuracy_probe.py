@@ -20,7 +20,7 @@ ld = lp.load_lut_dict(lut_dir("lerf-g"))
 ls = lp.LutSet(ld)
 lp.lib().lerf_debug_resize_variant(int(os.environ.get("ACC_VARIANT", "0")))  # int-scale kernel variant under test
 for name, img in (("uniform", uniform_image(3000, rows, 2040)), ("natural", natural_image(3001, min(rows, 400), 2040))):
-    for S in (4, 2):
+    for S in tuple(int(v) for v in os.environ.get("ACC_SCALES", "4,2").split(",")):
         t = time.time()
         ref, rfeat, rcodes = orc.lerf_sr(img, ld, S, S)
         t = time.time() - t
