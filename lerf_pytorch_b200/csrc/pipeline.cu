@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256, MINB) sr_pipeline_kernel(const __grid_con
   int bx, by, p;
   if (is3) {
     split_block(c3, a.r3.g, bx, by, p);
-    rsi::resize_int_body<S, FMT, 2>(a.r3.feat, a.r3.codes, a.H, a.W, a.oH, a.oW, a.r3.geom, a.r3.ct, a.r3.channels,
+    rsi::resize_int_body<S, FMT, 6>(a.r3.feat, a.r3.codes, a.H, a.W, a.oH, a.oW, a.r3.geom, a.r3.ct, a.r3.channels,
                                  a.r3.ly0, a.r3.oy0, a.r3.oy1, a.r3.out, bx, by, p, *reinterpret_cast<rsi::Smem*>(smem_raw));
     return;
   }
@@ -117,6 +117,7 @@ int run_pipeline(const lerf_luts_impl* L, const lerf_sr_plan_impl* P, const uint
   if (gsz > planes) gsz = planes;
   const int G = (planes + gsz - 1) / gsz;
 
+  if (!rsi::ref_tap_ok<S>(P)) return -1;  // the resampler role takes production's nearest-tap weights (resample_int.cuh MODE 6)
   PipeArgs<S> a;
   memset(&a, 0, sizeof(a));
   a.H = H; a.W = W; a.oH = P->oH; a.oW = P->oW;
@@ -125,7 +126,7 @@ int run_pipeline(const lerf_luts_impl* L, const lerf_sr_plan_impl* P, const uint
   a.r1.in = in; a.r1.ia = ia; a.r1.y0 = f0; a.r1.y1 = f1 + 1; a.r1.feat = feat;
   for (int i = 0; i < 6; ++i) a.r2.tabs.t[i] = L->mt2[i];
   a.r2.feat = feat; a.r2.y0 = c0; a.r2.y1 = c1 + 1; a.r2.codes = codes;
-  a.r3.feat = feat; a.r3.codes = codes; a.r3.geom = rsi::make_geom<S>(P, max_sigma, true); a.r3.ct = rsi::plan_coef_tabs(P, max_sigma, st);
+  a.r3.feat = feat; a.r3.codes = codes; a.r3.geom = rsi::make_geom<S>(P, max_sigma, true, /*signed_diff=*/true); a.r3.ct = rsi::plan_coef_tabs(P, max_sigma, st);
   if (!a.r3.ct) return fail(LERF_ECUDA, "uploading the hyper decode tables failed");
   a.r3.channels = ia.channels; a.r3.ly0 = ly0; a.r3.oy0 = oy0; a.r3.oy1 = oy1; a.r3.out = out;
   const int gx12 = (W + cellk::kTX - 1) / cellk::kTX;

@@ -84,7 +84,7 @@ static int launch_int(const lerf_sr_plan_impl* P, const uint8_t* feat, const uin
 #endif
   const bool prod = rv == 0 || rv == 7 || rv == 13;
   const bool cg = prod && geom_is_constexpr<S>(P);  // geometry factors as immediates (resample_int.cuh CGeom)
-  const bool ref = cg && (rv == 7 || (rv == 0 && kRefTapDefault));  // weights relative to the nearest tap (combine_ref)
+  const bool ref = prod && ref_tap_ok<S>(P) && (rv == 7 || (rv == 0 && kRefTapDefault));  // weights relative to the nearest tap (combine_ref)
   const IntGeom<S> g = make_geom<S>(P, max_sigma, /*unsigned_form=*/prod || rv == 4 || rv == 11, /*signed_diff=*/ref);
   const CoefTabs* ct = plan_coef_tabs(P, max_sigma, st);
   if (!ct) return fail(LERF_ECUDA, "uploading the hyper decode tables failed");
@@ -97,7 +97,8 @@ static int launch_int(const lerf_sr_plan_impl* P, const uint8_t* feat, const uin
   if (g_dbg.u8_staged && (prod || rv == 11)) {
     if constexpr (S == 4 || S == 8) {  // planar: aligned words through a lane shuffle (x4) or as they are (x8)
       if (fmt == LERF_OUT_U8 && g.ph_x == S / 2 && P->oW % 4 == 0 && ((uintptr_t)out & 3) == 0) {
-        if (ref) LERF_U8P(2);
+        if (ref && cg) LERF_U8P(3);
+        else if (ref) LERF_U8P(2);
         else if (cg) LERF_U8P(1);
         else LERF_U8P(0);
         LERF_LAUNCHED();
@@ -106,7 +107,8 @@ static int launch_int(const lerf_sr_plan_impl* P, const uint8_t* feat, const uin
     }
     if constexpr (S != 4 && S != 8) {  // planar at x2 / x3: the staged tile
       if (fmt == LERF_OUT_U8) {
-        if (ref) LERF_U8T(1, 2);
+        if (ref && cg) LERF_U8T(1, 3);
+        else if (ref) LERF_U8T(1, 2);
         else if (cg) LERF_U8T(1, 1);
         else LERF_U8T(1, 0);
         LERF_LAUNCHED();
@@ -117,6 +119,7 @@ static int launch_int(const lerf_sr_plan_impl* P, const uint8_t* feat, const uin
       if (fmt == LERF_OUT_U8_HWC && channels == 3 && planes % 3 == 0) {
         grid.z = planes / 3;
         if (g_dbg.resize_variant == 12) resize_sr_int_gauss_u8_kernel<S, 3, 0, false><<<grid, block, 0, st>>>(feat, codes, P->H, P->W, P->oH, P->oW, g, ct, ly0, oy0, oy1, (unsigned char*)out);
+        else if (ref && cg) LERF_U8T(3, 3);
         else if (ref) LERF_U8T(3, 2);
         else if (cg) LERF_U8T(3, 1);
         else LERF_U8T(3, 0);
@@ -136,13 +139,15 @@ static int launch_int(const lerf_sr_plan_impl* P, const uint8_t* feat, const uin
   else if (g_dbg.resize_variant == 2) LERF_GK(F, 0, 4);         \
   else if (g_dbg.resize_variant == 5) LERF_GK(F, 0, 5);         \
   else if (g_dbg.resize_variant == 4) LERF_GK(F, 2, 5);         \
-  else if (ref) LERF_GK(F, 5, 4);                               \
+  else if (ref && cg) LERF_GK(F, 5, 4);                         \
+  else if (ref) LERF_GK(F, 6, 4);                               \
   else if (cg) LERF_GK(F, 3, 4);                                \
   else LERF_GK(F, 2, 4)
 #else
 #define LERF_GO(F)               \
-  if (ref) LERF_GK(F, 5, 4);     \
-  else if (cg) LERF_GK(F, 3, 4); \
+  if (ref && cg) LERF_GK(F, 5, 4); \
+  else if (ref) LERF_GK(F, 6, 4);  \
+  else if (cg) LERF_GK(F, 3, 4);   \
   else LERF_GK(F, 2, 4)
 #endif
   switch (fmt) {

@@ -253,9 +253,9 @@ __device__ __forceinline__ void resize_int_body(const uint8_t* __restrict__ feat
   long long rowh = ((long long)(p / channels) * oH + oyb) * oW;     // same for the interleaved layout
   const bool full = oxb >= 0 && oxb + S <= oW;
   constexpr bool kHoist = MODE == 1 && S <= 4;
-  constexpr bool kRowQ = MODE == 2 || MODE == 3 || MODE == 5;  // S = 8 would need 64 registers for the column terms
-  constexpr bool kCG = MODE == 3 || MODE == 5;                 // geometry factors as immediates (CGeom)
-  constexpr bool kRef = MODE == 5;                             // weights relative to the phase's nearest tap (combine_ref)
+  constexpr bool kRowQ = MODE == 2 || MODE == 3 || MODE == 5 || MODE == 6;  // S = 8 would need 64 registers for the column terms
+  constexpr bool kCG = MODE == 3 || MODE == 5;                              // geometry factors as immediates (CGeom)
+  constexpr bool kRef = MODE == 5 || MODE == 6;                             // weights relative to the phase's nearest tap (combine_ref)
   double colq[kHoist ? 4 : 1][kHoist ? S : 1];
   if (kHoist) {
 #pragma unroll
@@ -304,14 +304,14 @@ __device__ __forceinline__ void resize_int_body(const uint8_t* __restrict__ feat
       }
       if (kRowQ) {
         const unsigned uq[4] = {(unsigned)q[0], (unsigned)q[1], (unsigned)q[2], (unsigned)q[3]};
-        if (FMT == LERF_OUT_F32 && kRef) {  // CGeom phases: tap (a, b) = (mc >= S/2, mr >= S/2) is the nearest one
-          if (mc * 2 >= S) res[mc] = mr * 2 >= S ? combine_ref<3>(uq, dv, v0, g.inv_scale) : combine_ref<2>(uq, dv, v0, g.inv_scale);
-          else res[mc] = mr * 2 >= S ? combine_ref<1>(uq, dv, v0, g.inv_scale) : combine_ref<0>(uq, dv, v0, g.inv_scale);
+        if (FMT == LERF_OUT_F32 && kRef) {  // centred phases: tap (a, b) = (2 mc + 1 >= S, 2 mr + 1 >= S) is the nearest one (ref_tap_ok)
+          if (mc * 2 + 1 >= S) res[mc] = mr * 2 + 1 >= S ? combine_ref<3>(uq, dv, v0, g.inv_scale) : combine_ref<2>(uq, dv, v0, g.inv_scale);
+          else res[mc] = mr * 2 + 1 >= S ? combine_ref<1>(uq, dv, v0, g.inv_scale) : combine_ref<0>(uq, dv, v0, g.inv_scale);
         } else if (kRef) {  // uint8 formats that do not take a staged kernel (x8 interleaved): the same weights
           const float v0m = v0 + kRoundMagic;
           uint32_t bits;
-          if (mc * 2 >= S) bits = mr * 2 >= S ? combine_ref_u8<3>(uq, dv, v0m, g.inv_scale) : combine_ref_u8<2>(uq, dv, v0m, g.inv_scale);
-          else bits = mr * 2 >= S ? combine_ref_u8<1>(uq, dv, v0m, g.inv_scale) : combine_ref_u8<0>(uq, dv, v0m, g.inv_scale);
+          if (mc * 2 + 1 >= S) bits = mr * 2 + 1 >= S ? combine_ref_u8<3>(uq, dv, v0m, g.inv_scale) : combine_ref_u8<2>(uq, dv, v0m, g.inv_scale);
+          else bits = mr * 2 + 1 >= S ? combine_ref_u8<1>(uq, dv, v0m, g.inv_scale) : combine_ref_u8<0>(uq, dv, v0m, g.inv_scale);
           res[mc] = (float)(bits & 255u);
         } else if (FMT == LERF_OUT_F32) res[mc] = combine_uq(uq, dv, v0, g.inv_scale);
         else res[mc] = (float)(combine_uq_u8(uq, dv, v0 + kRoundMagic, g.inv_scale) & 255u);  // one rounding, like every uint8 epilogue (r2)
@@ -374,8 +374,8 @@ __device__ __forceinline__ uint32_t to_u8_sat(float v) {  // clip(round_half_eve
 
 // The ROWQ arithmetic of resize_int_body for one cell: `emit(mr, res)` receives the S samples of output row oyb + mr.
 // (uint8 flavour: res[mc] carries the rounded sample in its low byte, see combine_uq_u8.)
-// CG: 0 = geometry factors from the kernel parameters, 1 = immediates (CGeom), 2 = immediates + weights relative to the
-// phase's nearest tap (combine_ref_u8).
+// CG: bit 0 = geometry factors as immediates (CGeom) instead of kernel parameters, bit 1 = weights relative to the phase's
+// nearest tap (combine_ref_u8) instead of the smallest exponent.
 template <int S, int CG, typename Emit>
 __device__ __forceinline__ void gauss_cell_rowq(const Smem& sm, const IntGeom<S>& g, int tx, int ty, int oyb, int oy0, int oy1,
                                                 Emit emit) {
@@ -399,20 +399,20 @@ __device__ __forceinline__ void gauss_cell_rowq(const Smem& sm, const IntGeom<S>
     if (oy < oy0 || oy >= oy1) continue;
     double rowa[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) rowa[t] = fma(ca[t], geom_xr<S, CG != 0>(g, mr, t & 1), g.magic);
+    for (int t = 0; t < 4; ++t) rowa[t] = fma(ca[t], geom_xr<S, (CG & 1) != 0>(g, mr, t & 1), g.magic);
     uint32_t res[S];
 #pragma unroll
     for (int mc = 0; mc < S; ++mc) {
       unsigned uq[4];
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        double e = fma(cc[t], geom_xc<S, CG != 0>(g, mc, t >> 1), rowa[t]);
-        e = fma(cb[t], geom_pp<S, CG != 0>(g, mr, mc, t & 1, t >> 1), e);
+        double e = fma(cc[t], geom_xc<S, (CG & 1) != 0>(g, mc, t >> 1), rowa[t]);
+        e = fma(cb[t], geom_pp<S, (CG & 1) != 0>(g, mr, mc, t & 1, t >> 1), e);
         uq[t] = (unsigned)__double2loint(e);
       }
-      if (CG == 2) {  // CGeom phases: tap (a, b) = (mc >= S/2, mr >= S/2) is the nearest one
-        if (mc * 2 >= S) res[mc] = mr * 2 >= S ? combine_ref_u8<3>(uq, dv, v0m, g.inv_scale) : combine_ref_u8<2>(uq, dv, v0m, g.inv_scale);
-        else res[mc] = mr * 2 >= S ? combine_ref_u8<1>(uq, dv, v0m, g.inv_scale) : combine_ref_u8<0>(uq, dv, v0m, g.inv_scale);
+      if (CG & 2) {  // centred phases: tap (a, b) = (2 mc + 1 >= S, 2 mr + 1 >= S) is the nearest one (ref_tap_ok)
+        if (mc * 2 + 1 >= S) res[mc] = mr * 2 + 1 >= S ? combine_ref_u8<3>(uq, dv, v0m, g.inv_scale) : combine_ref_u8<2>(uq, dv, v0m, g.inv_scale);
+        else res[mc] = mr * 2 + 1 >= S ? combine_ref_u8<1>(uq, dv, v0m, g.inv_scale) : combine_ref_u8<0>(uq, dv, v0m, g.inv_scale);
       } else {
         res[mc] = combine_uq_u8(uq, dv, v0m, g.inv_scale);
       }
@@ -671,6 +671,18 @@ inline IntGeom<S> make_geom(const lerf_sr_plan_impl* P, float max_sigma, bool un
   g.ph_y = P->ph_y;
   g.ph_x = P->ph_x;
   return g;
+}
+
+// true when, for every phase m, tap k = (2m + 1 >= S) is the nearest one (|distance| <= 1/2) on both axes: the condition of
+// the nearest-tap weights (combine_ref).  Holds for the geometry of out = S * in: even S have phases (2m+1)/(2S), x3 has
+// 1/3, 2/3 (-1/3 to the second tap) and 1 (0 to the second tap).
+template <int S>
+inline bool ref_tap_ok(const lerf_sr_plan_impl* P) {
+  for (int m = 0; m < S; ++m) {
+    const int k = 2 * m + 1 >= S ? 1 : 0;
+    if (fabs(P->ph_dist_y[m][k]) > 0.5 + 1e-9 || fabs(P->ph_dist_x[m][k]) > 0.5 + 1e-9) return false;
+  }
+  return true;
 }
 
 // true when the plan's float64 phase distances are exactly CGeom<S>'s (even S, out = S * in)

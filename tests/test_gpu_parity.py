@@ -364,7 +364,7 @@ def test_pipeline_kernel_equals_three_launches(lp, luts, fmt):
         L.lerf_debug_pipeline(0, 4, 0)
 
 
-@pytest.mark.parametrize("S", [4, 2, 8])
+@pytest.mark.parametrize("S", [4, 2, 8, 3])
 def test_resize_kernel_variants_within_tolerance(lp, orc, luts, S):
     ld, ls = luts["g"]
     img = uniform_image(61 + S, 50, 47)
