@@ -3,10 +3,7 @@
 set -e
 cd "$(dirname "$0")/.."
 cp gpurun_out/bench_r2_n1.json gpurun_out/bench_r2_reference.json gpurun_out/r2_configs.jsonl gpurun_out/r2_ncu_launches.csv profiles/
-python scripts/ncu_summary.py gpurun_out/r2_prof.ncu-rep profiles/r2_ncu_summary.md "r2: the three production kernels at the bench's launch size (8 frames 2040x1356, natural-like input)"
-python scripts/ncu_summary.py gpurun_out/r2_prof_uniform.ncu-rep profiles/r2_ncu_uniform_summary.md "r2: the same kernels on uniform-random input"
-python scripts/ncu_summary.py gpurun_out/r2_prof_u8.ncu-rep profiles/r2_ncu_u8_summary.md "r2: the uint8 epilogue kernels (planar through a lane shuffle, HWC through a staged tile)"
-python scripts/ncu_traffic.py gpurun_out/r2_prof.ncu-rep profiles/traffic.json > /dev/null
+cp gpurun_out/r2_ncu_summary.md gpurun_out/r2_ncu_uniform_summary.md gpurun_out/r2_ncu_u8_summary.md gpurun_out/traffic.json profiles/  # written on the box
 python - <<'PY'
 import json, subprocess
 d = json.load(open("profiles/bench_r2_n1.json"))

@@ -16,3 +16,9 @@ ncu --set full --clock-control none -k regex:"resize_sr_int_gauss_u8" -c 2 -f -o
   python bench.py --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 0 --no-parity-check > gpurun_out/r2_prof_u8.log 2>&1; tail -1 gpurun_out/r2_prof_u8.log | cut -c1-100
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"lut_|resize_sr|warp_" -c 400 --csv --log-file gpurun_out/r2_ncu_launches.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 --no-extra-arms --no-parity-check > gpurun_out/r2_launch.log 2>&1; tail -1 gpurun_out/r2_launch.log | cut -c1-200
+# gpurun merges at most 64 MiB back: summarise the captures here and keep only the main report
+python scripts/ncu_summary.py gpurun_out/r2_prof.ncu-rep gpurun_out/r2_ncu_summary.md "r2: the three production kernels at the bench's launch size (8 frames 2040x1356, natural-like input)" > /dev/null
+python scripts/ncu_summary.py gpurun_out/r2_prof_uniform.ncu-rep gpurun_out/r2_ncu_uniform_summary.md "r2: the same kernels on uniform-random input" > /dev/null
+python scripts/ncu_summary.py gpurun_out/r2_prof_u8.ncu-rep gpurun_out/r2_ncu_u8_summary.md "r2: the uint8 epilogue kernels (planar through a lane shuffle, HWC through a staged tile)" > /dev/null
+python scripts/ncu_traffic.py gpurun_out/r2_prof.ncu-rep gpurun_out/traffic.json > /dev/null
+rm -f gpurun_out/r2_prof_uniform.ncu-rep gpurun_out/r2_prof_u8.ncu-rep
