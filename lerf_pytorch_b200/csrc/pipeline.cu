@@ -117,7 +117,7 @@ int run_pipeline(const lerf_luts_impl* L, const lerf_sr_plan_impl* P, const uint
   if (gsz > planes) gsz = planes;
   const int G = (planes + gsz - 1) / gsz;
 
-  if (!rsi::ref_tap_ok<S>(P)) return -1;  // the resampler role takes production's nearest-tap weights (resample_int.cuh MODE 6)
+  if (!rsi::ref_tap_ok<S>(P, max_sigma)) return -1;  // the resampler role takes production's nearest-tap weights (resample_int.cuh MODE 6)
   PipeArgs<S> a;
   memset(&a, 0, sizeof(a));
   a.H = H; a.W = W; a.oH = P->oH; a.oW = P->oW;

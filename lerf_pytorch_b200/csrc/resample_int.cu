@@ -84,8 +84,13 @@ static int launch_int(const lerf_sr_plan_impl* P, const uint8_t* feat, const uin
 #endif
   const bool prod = rv == 0 || rv == 7 || rv == 13;
   const bool cg = prod && geom_is_constexpr<S>(P);  // geometry factors as immediates (resample_int.cuh CGeom)
-  const bool ref = prod && ref_tap_ok<S>(P) && (rv == 7 || (rv == 0 && kRefTapDefault));  // weights relative to the nearest tap (combine_ref)
-  const IntGeom<S> g = make_geom<S>(P, max_sigma, /*unsigned_form=*/prod || rv == 4 || rv == 11, /*signed_diff=*/ref);
+  bool ref = prod && ref_tap_ok<S>(P, max_sigma) && (rv == 7 || (rv == 0 && kRefTapDefault));  // weights relative to the nearest tap (combine_ref)
+  IntGeom<S> g = make_geom<S>(P, max_sigma, /*unsigned_form=*/prod || rv == 4 || rv == 11, /*signed_diff=*/ref);
+  if (ref && g.fb < kMinFracBits) {  // the signed differences cost a bit: the minimum form keeps it
+    ref = false;
+    g = make_geom<S>(P, max_sigma, true, false);
+  }
+  if (prod && g.fb < kMinFracBits) return -1;  // too wide an exponent range for the fixed point (large max_sigma): next kernel
   const CoefTabs* ct = plan_coef_tabs(P, max_sigma, st);
   if (!ct) return fail(LERF_ECUDA, "uploading the hyper decode tables failed");
   // cell rows touched by the output band

@@ -23,6 +23,10 @@ namespace lerf {
 namespace rsi {
 
 constexpr double kLog2e = 1.4426950408889634;
+// The fixed-point exponent of the fast resamplers is rounded (up to three times) at 2^-FB: with FB = 23 that is 1.2e-7 of a
+// weight, 3e-5 of an output sample in the worst case, on top of ex2.approx's 6e-5 -- inside the 1e-4 bar.  A plan whose
+// exponent range (max_sigma, distances) leaves fewer bits goes to the next kernel down, in the end the float64 one.
+constexpr int kMinFracBits = 23;
 
 template <int S>
 struct IntGeom {
@@ -34,6 +38,7 @@ struct IntGeom {
   double magic;           // 1.5 * 2^(52 - FB)
   float inv_scale;        // 2^-FB
   int ph_y, ph_x;         // first output of cell l is S*l + ph
+  int fb;                 // fraction bits of the fixed-point exponent (host only: the launchers require >= kMinFracBits)
 };
 
 // Compile-time geometry of out = S * in for even S (r2): the distances of output S*l + S/2 + m to its two taps are
@@ -651,6 +656,7 @@ inline IntGeom<S> make_geom(const lerf_sr_plan_impl* P, float max_sigma, bool un
     while (fb > 8 && bound * (double)(1u << fb) >= (signed_diff ? 2147483000.0 : 4294967000.0)) --fb;
     g.magic = (double)(1ull << (52 - fb)) + 16.0 / (double)(1u << fb);
     g.inv_scale = -1.0f / (float)(1u << fb);
+    g.fb = fb;
     for (int m = 0; m < S; ++m)
       for (int k = 0; k < 2; ++k) {
         g.xr[m][k] = -g.xr[m][k];
@@ -668,6 +674,7 @@ inline IntGeom<S> make_geom(const lerf_sr_plan_impl* P, float max_sigma, bool un
   while (fb > 8 && bound * (double)(1u << fb) >= 2147483000.0) --fb;
   g.magic = 1.5 * (double)(1ull << (52 - fb));
   g.inv_scale = 1.0f / (float)(1u << fb);
+  g.fb = fb;
   g.ph_y = P->ph_y;
   g.ph_x = P->ph_x;
   return g;
@@ -677,7 +684,10 @@ inline IntGeom<S> make_geom(const lerf_sr_plan_impl* P, float max_sigma, bool un
 // the nearest-tap weights (combine_ref).  Holds for the geometry of out = S * in: even S have phases (2m+1)/(2S), x3 has
 // 1/3, 2/3 (-1/3 to the second tap) and 1 (0 to the second tap).
 template <int S>
-inline bool ref_tap_ok(const lerf_sr_plan_impl* P) {
+inline bool ref_tap_ok(const lerf_sr_plan_impl* P, float max_sigma) {
+  // the reference tap's own -log2 w is at most L/2 (sigma (1/2 + 1/2))^2: the other weights, relative to it, reach 2^that and
+  // the numerator 765 times more -- keep it below 2^100 (sigma <= 11.7; the models use 10), else the minimum form
+  if (0.5 * kLog2e * (double)max_sigma * (double)max_sigma > 100.0) return false;
   for (int m = 0; m < S; ++m) {
     const int k = 2 * m + 1 >= S ? 1 : 0;
     if (fabs(P->ph_dist_y[m][k]) > 0.5 + 1e-9 || fabs(P->ph_dist_x[m][k]) > 0.5 + 1e-9) return false;

@@ -35,6 +35,7 @@ constexpr int kWX = 33, kWY = 33;   // input window capacity; a block covers as 
                                     // as keep its taps inside 33 input rows, so the per-block set-up is amortised
 
 struct FixQ {
+  int fb;           // fraction bits (host only)
   double magic;     // 2^(52-FB) + 16 * 2^-FB
   float neg_scale;  // -2^-FB
   double dlim;      // warp: distances are clamped to +-dlim for the exponent (only outside the validity mask)
@@ -47,6 +48,7 @@ FixQ make_fixq(float max_sigma) {
   const double bound = 0.5 * kLog2e * reach * reach + 2.0;
   int fb = 26;
   while (fb > 8 && bound * (double)(1u << fb) >= 4294967000.0) --fb;
+  q.fb = fb;
   q.magic = (double)(1ull << (52 - fb)) + 16.0 / (double)(1u << fb);
   q.neg_scale = -1.0f / (float)(1u << fb);
   return q;
@@ -582,6 +584,7 @@ int resize_sr_tile(int kind, const lerf_sr_plan_impl* P, const uint8_t* feat, co
                    float max_sigma, int oy0, int oy1, void* out, int fmt, cudaStream_t st) {
   if (!P->tile_ok || !(max_sigma >= 0.0f) || max_sigma > 64.0f) return -1;
   const FixQ fq = make_fixq(max_sigma);
+  if (kind == LERF_KIND_GAUSS && fq.fb < kMinFracBits) return -1;  // too wide an exponent range for the fixed point: the float64 kernels take it
   const CoefTabs* ct = nullptr;
   if (kind == LERF_KIND_GAUSS) {
     ct = plan_coef_tabs(P, max_sigma, st);
@@ -619,6 +622,7 @@ int resize_sr_cell(int kind, const lerf_sr_plan_impl* P, const uint8_t* feat, co
   if (!any_scale && (P->oW < 3 * (long long)P->W || P->oH < 3 * (long long)P->H)) return -1;
   if (!P->tile_ok || !P->cell_x || P->cell_max_x > 4 || P->cell_max_y > kCellMaxY || !(max_sigma >= 0.0f) || max_sigma > 64.0f) return -1;
   const FixQ fq = make_fixq(max_sigma);
+  if (kind == LERF_KIND_GAUSS && fq.fb < kMinFracBits) return -1;  // too wide an exponent range for the fixed point: the float64 kernels take it
   const CoefTabs* ct = nullptr;
   if (kind == LERF_KIND_GAUSS) {
     ct = plan_coef_tabs(P, max_sigma, st);
@@ -686,6 +690,7 @@ int warp_fast(int kind, const uint8_t* feat, const uint8_t* codes, int planes, i
   g.H = H; g.W = W; g.oH = oH; g.oW = oW;
   g.pad0_y = pad0_y; g.pad0_x = pad0_x; g.mpad0_y = mpad0_y; g.mpad0_x = mpad0_x; g.border = border;
   const FixQ fq = make_fixq(max_sigma);
+  if (kind == LERF_KIND_GAUSS && fq.fb < kMinFracBits) return -1;  // too wide an exponent range for the fixed point: the float64 kernels take it
   dim3 block(32, 8), grid((oW + 31) / 32, (oH + 7) / 8, 1);
   // Gaussian: decode every input sample once into a 32-byte record (stream-ordered scratch), then gather records.
   TapRec* rec = nullptr;

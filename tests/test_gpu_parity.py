@@ -387,6 +387,26 @@ def test_resize_kernel_variants_within_tolerance(lp, orc, luts, S):
         L.lerf_debug_resize_variant(0)
 
 
+@pytest.mark.parametrize("max_sigma", [1.0, 4.0, 10.0, 11.5, 12.0, 30.0, 64.0])
+def test_integer_scale_kernels_over_max_sigma(lp, orc, luts, max_sigma):
+    """--maxSigma other than 10: the nearest-tap weights of the integer-scale kernels hold while the reference tap's own
+    exponent stays below 100 (sigma <= 11.7); above, the launcher takes the minimum form.  Both sides of the switch, all
+    formats, against the oracle: finite everywhere, within the bars."""
+    ld, ls = luts["g"]
+    img = uniform_image(70 + int(max_sigma), 41, 39)
+    for S in (4, 3):
+        ref, _, _ = orc.lerf_sr(img, ld, S, S, max_sigma=max_sigma)
+        sr = lp.LerfSR(ls, S, max_sigma=max_sigma)
+        out = sr(_cuda(img), out_format="f32").cpu().numpy()
+        assert np.isfinite(out).all()
+        assert _maxabs(out, ref) <= FP32_TOL, (S, max_sigma)
+        want = orc.to_uint8_hwc(ref)
+        for fmt in ("u8", "u8_hwc"):
+            u8 = sr(_cuda(img), out_format=fmt).cpu().numpy()
+            u8 = np.transpose(u8, (1, 2, 0)) if fmt == "u8" else u8
+            assert np.abs(u8.astype(int) - want.astype(int)).max() <= 1, (S, max_sigma, fmt)
+
+
 def test_warp_vs_oracle_random_homographies(lp, orc, luts):
     """cfg-4-like: random in-scale / out-of-scale homographies (SURVEY 8d generator) on a synthetic input."""
     rng = np.random.default_rng(4000)
