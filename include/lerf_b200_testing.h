@@ -40,7 +40,7 @@ void lerf_debug_force_generic(int on);
  * is one 256-bit gather; 0 = taps are gathered from feat/codes and decoded through tables.  Identical results. */
 void lerf_debug_warp_records(int on);
 
-/* Integer-scale resampler: 0 = production (weights relative to the phase's NEAREST tap, whose weight is
+/* Integer-scale resampler: 0 = production (weights relative to the phase's NEAREST tap where the plan allows it, whose weight is
  * exactly 1 -- no minimum over the taps, one exponential less per sample); 13 = weights relative to the smallest exponent
  * (production until r2g; still what the tile / cell kernels do); 7 = the nearest-tap form by name;
  * 10 = production arithmetic with the byte-store uint8 epilogue of round 1;
